@@ -1,0 +1,183 @@
+// bn.cu -- batch-norm statistics plumbing (per event of 40 images).
+// layers.py:656-689 (ccbn.forward), :728-742 (bn.forward), F.batch_norm semantics:
+// normalise with the biased batch variance, running_var gets the unbiased one, momentum 0.1.
+// The heavy passes (sums in the producer epilogue, apply in the consumer prologue) live in
+// the conv kernels; these kernels are the tiny per-(event, channel) glue around them.
+#include "common.cuh"
+using namespace iea;
+
+namespace {
+
+// partials[e][t][c][2]; grid (events*tiles, channel chunks)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const void* x, int x_dtype, int x_ld, int rows_per_event, int c,
+                                                       int tiles, float* partials, int cb) {
+  __shared__ float r1[256], r2[256];
+  const int e = blockIdx.x / tiles, t = blockIdx.x % tiles;
+  const int rows_per_tile = (rows_per_event + tiles - 1) / tiles;
+  const int64_t r0 = (int64_t)e * rows_per_event + (int64_t)t * rows_per_tile;
+  int64_t r1e = r0 + rows_per_tile;
+  const int64_t rend = (int64_t)(e + 1) * rows_per_event;
+  if (r1e > rend) r1e = rend;
+  const int lanes = 256 / cb;
+  const int cl = threadIdx.x % cb, pl = threadIdx.x / cb;
+  const int cc = blockIdx.y * cb + cl;
+  float s1 = 0.f, s2 = 0.f;
+  if (cc < c && pl < lanes)
+    for (int64_t m = r0 + pl; m < r1e; m += lanes) {
+      float v = ld_act(x, x_dtype, m * x_ld + cc);
+      s1 += v;
+      s2 = fmaf(v, v, s2);
+    }
+  r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+  __syncthreads();
+  if (pl == 0 && cc < c) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) { a += r1[l * cb + cl]; b += r2[l * cb + cl]; }
+    float* o = partials + (((int64_t)e * tiles + t) * c + cc) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+// one thread per channel; events handled sequentially so the running statistics see them in order
+__global__ void bn_finalize_kernel(const float* partials, int events, int tiles, double count, int imgs, int c,
+                                   const float* gain, int64_t gain_ld, float gain_add, const float* bias,
+                                   int64_t bias_ld, float* stored_mean, float* stored_var, int training,
+                                   float momentum, float eps, float* mean_out, float* rstd_out, float* scale,
+                                   float* shift) {
+  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc >= c) return;
+  float rm = stored_mean ? stored_mean[cc] : 0.f, rv = stored_var ? stored_var[cc] : 1.f;
+  for (int e = 0; e < events; ++e) {
+    float mean, rstd;
+    if (training) {
+      double s1 = 0.0, s2 = 0.0;
+      const float* p = partials + ((int64_t)e * tiles * c + cc) * 2;
+      for (int t = 0; t < tiles; ++t, p += (int64_t)c * 2) { s1 += (double)p[0]; s2 += (double)p[1]; }
+      double m = s1 / count;
+      double var = s2 / count - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+      double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+      rm = (1.f - momentum) * rm + momentum * mean;
+      rv = (1.f - momentum) * rv + momentum * (float)unb;
+    } else {
+      mean = rm;
+      rstd = rsqrtf(rv + eps);
+    }
+    if (mean_out) { mean_out[e * c + cc] = mean; rstd_out[e * c + cc] = rstd; }
+    for (int i = 0; i < imgs; ++i) {
+      int64_t n = (int64_t)e * imgs + i;
+      float gn = gain_add + (gain ? gain[n * gain_ld + cc] : 0.f);
+      float bs = bias ? bias[n * bias_ld + cc] : 0.f;
+      float sc = rstd * gn;
+      scale[n * c + cc] = sc;
+      shift[n * c + cc] = bs - mean * sc;
+    }
+  }
+  if (training && stored_mean) { stored_mean[cc] = rm; stored_var[cc] = rv; }
+}
+
+__global__ void bn_finalize_bwd_kernel(const float* dscale, const float* dshift, const float* scale,
+                                       const float* mean, const float* rstd, int events, int imgs, double count,
+                                       int c, const float* gain, int64_t gain_ld, float gain_add, float* dgain,
+                                       int64_t dgain_ld, float* dbias, int64_t dbias_ld, int reduce_over_n,
+                                       int training, float* ds1, float* ds2) {
+  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc >= c) return;
+  float dg_tot = 0.f, db_tot = 0.f;
+  for (int e = 0; e < events; ++e) {
+    const float mu = mean[e * c + cc], rs = rstd[e * c + cc];
+    float dmean = 0.f, drstd = 0.f;
+    for (int i = 0; i < imgs; ++i) {
+      int64_t n = (int64_t)e * imgs + i;
+      float dsc = dscale[n * c + cc], dsh = dshift[n * c + cc];
+      float gn = gain_add + (gain ? gain[n * gain_ld + cc] : 0.f);
+      // scale = rstd*gn ; shift = bias - mean*scale
+      float dsc_tot = dsc - mu * dsh;          // through shift
+      float dgn = rs * dsc_tot;
+      drstd += gn * dsc_tot;
+      dmean -= dsh * scale[n * c + cc];
+      if (reduce_over_n) { dg_tot += dgn; db_tot += dsh; }
+      else {
+        if (dgain) dgain[n * dgain_ld + cc] = dgn;
+        if (dbias) dbias[n * dbias_ld + cc] = dsh;
+      }
+    }
+    if (ds1) {
+      float a = 0.f, b = 0.f;
+      if (training) {
+        // rstd = (var+eps)^-1/2, var = S2/M - mean^2, mean = S1/M
+        double dvar = -0.5 * (double)drstd * (double)rs * (double)rs * (double)rs;
+        double dm = (double)dmean - 2.0 * (double)mu * dvar;
+        a = (float)(dm / count);
+        b = (float)(dvar / count);
+      }
+      ds1[e * c + cc] = a;
+      ds2[e * c + cc] = b;
+    }
+  }
+  if (reduce_over_n) {
+    if (dgain) dgain[cc] = dg_tot;
+    if (dbias) dbias[cc] = db_tot;
+  }
+}
+
+__global__ void affine_act_kernel(const void* x, int x_dtype, const float* scale, const float* shift, int64_t n,
+                                  int64_t hw, int c, int relu, void* y, int y_dtype) {
+  const int64_t total = n * hw * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cc = i % c;
+    int64_t nn = i / ((int64_t)hw * c);
+    float v = fmaf(ld_act(x, x_dtype, i), scale[nn * c + cc], shift[nn * c + cc]);
+    if (relu) v = fmaxf(v, 0.f);
+    st_act(y, y_dtype, i, v);
+  }
+}
+
+}  // namespace
+
+extern "C" int iea_bn_stats(const void* x, int x_dtype, int x_ld, int64_t rows, int rows_per_event, int c,
+                            int tiles_per_event, float* partials, iea_stream_t stream) {
+  IEA_CHECK_ARG(rows % rows_per_event == 0, "iea_bn_stats: rows (%lld) not a multiple of rows_per_event (%d)",
+                (long long)rows, rows_per_event);
+  int events = (int)(rows / rows_per_event);
+  int cb = 1;
+  while (cb < c && cb < 32) cb <<= 1;
+  dim3 grid(events * tiles_per_event, cdiv(c, cb));
+  bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_dtype, x_ld, rows_per_event, c, tiles_per_event,
+                                                           partials, cb);
+  return check_launch("iea_bn_stats");
+}
+
+extern "C" int iea_bn_finalize(const float* partials, int events, int tiles_per_event, int64_t count_per_event,
+                               int imgs_per_event, int c, const float* gain, int64_t gain_ld, float gain_add,
+                               const float* bias, int64_t bias_ld, float* stored_mean, float* stored_var,
+                               int training, float momentum, float eps, float* mean_out, float* rstd_out,
+                               float* scale, float* shift, iea_stream_t stream) {
+  bn_finalize_kernel<<<cdiv(c, 64), 64, 0, (cudaStream_t)stream>>>(
+      partials, events, tiles_per_event, (double)count_per_event, imgs_per_event, c, gain, gain_ld, gain_add, bias,
+      bias_ld, stored_mean, stored_var, training, momentum, eps, mean_out, rstd_out, scale, shift);
+  return check_launch("iea_bn_finalize");
+}
+
+extern "C" int iea_bn_finalize_bwd(const float* dscale, const float* dshift, const float* scale, const float* mean,
+                                   const float* rstd, int events, int imgs_per_event, int64_t count_per_event, int c,
+                                   const float* gain, int64_t gain_ld, float gain_add, float* dgain, int64_t dgain_ld,
+                                   float* dbias, int64_t dbias_ld, int reduce_over_n, int training, float* ds1,
+                                   float* ds2, iea_stream_t stream) {
+  bn_finalize_bwd_kernel<<<cdiv(c, 64), 64, 0, (cudaStream_t)stream>>>(
+      dscale, dshift, scale, mean, rstd, events, imgs_per_event, (double)count_per_event, c, gain, gain_ld, gain_add,
+      dgain, dgain_ld, dbias, dbias_ld, reduce_over_n, training, ds1, ds2);
+  return check_launch("iea_bn_finalize_bwd");
+}
+
+extern "C" int iea_affine_act(const void* x, int x_dtype, const float* scale, const float* shift, int64_t n,
+                              int64_t hw, int c, int relu, void* y, int y_dtype, iea_stream_t stream) {
+  int64_t total = n * hw * c;
+  int64_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  affine_act_kernel<<<(int)(b < 1 ? 1 : b), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, scale, shift, n, hw, c, relu,
+                                                                          y, y_dtype);
+  return check_launch("iea_affine_act");
+}

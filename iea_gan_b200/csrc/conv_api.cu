@@ -1,0 +1,35 @@
+// conv_api.cu -- iea_conv_fprop: validates the descriptor and dispatches to the tcgen05
+// implicit-GEMM kernel (conv_tc.cu) or to the shape-generic kernel (conv_generic.cu).
+#include "common.cuh"
+#include <stdlib.h>
+using namespace iea;
+
+int iea_conv_fprop_generic(const iea_conv_desc* d, cudaStream_t s);
+int iea_conv_fprop_tc(const iea_conv_desc* d, cudaStream_t s);
+int iea_conv_tc_ok(const iea_conv_desc* d);
+
+static int validate(const iea_conv_desc* d) {
+  IEA_CHECK_ARG(d != nullptr, "iea_conv_fprop: null descriptor");
+  IEA_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "iea_conv_fprop: ksize %d not built (1 or 3)", d->ksize);
+  IEA_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "iea_conv_fprop: empty geometry");
+  IEA_CHECK_ARG(d->x && d->wpack && d->y, "iea_conv_fprop: null tensor pointer");
+  IEA_CHECK_ARG(d->in_mode != IEA_IN_UP2 || (d->h % 2 == 0 && d->w % 2 == 0), "iea_conv_fprop: up2 needs even h,w");
+  IEA_CHECK_ARG((d->in_scale == nullptr) == (d->in_shift == nullptr), "iea_conv_fprop: in_scale/in_shift mismatch");
+  IEA_CHECK_ARG(d->x_ld >= d->cin && d->y_ld >= 1, "iea_conv_fprop: bad pixel strides");
+  return 0;
+}
+
+extern "C" int iea_conv_tc_supported(const iea_conv_desc* d) { return iea_conv_tc_ok(d); }
+
+extern "C" int iea_conv_fprop(const iea_conv_desc* d, iea_stream_t stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d->impl == IEA_IMPL_GENERIC) return iea_conv_fprop_generic(d, s);
+  if (d->impl == IEA_IMPL_TCGEN05) {
+    IEA_CHECK_ARG(iea_conv_tc_ok(d), "iea_conv_fprop: tcgen05 path requested for an unsupported shape "
+                  "(cin=%d cout=%d k=%d)", d->cin, d->cout, d->ksize);
+    return iea_conv_fprop_tc(d, s);
+  }
+  return iea_conv_tc_ok(d) ? iea_conv_fprop_tc(d, s) : iea_conv_fprop_generic(d, s);
+}

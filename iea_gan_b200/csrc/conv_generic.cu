@@ -1,0 +1,415 @@
+// conv_generic.cu -- shape-generic fused convolution kernels on the CUDA cores.
+//
+// These cover every shape the nets contain (Cin = 1 input conv, Cout = 1 output conv,
+// odd K of linear_f, tiny spatial sizes) and serve as the in-library cross-check of the
+// tcgen05 path (conv_tc.cu), which takes the tensor-core-eligible layers.  Same fused
+// semantics as iea_conv_desc documents: prologue T(x) = [pool|up](relu(x*scale+shift)),
+// epilogue act(acc*out_scale + bias + residual) and per-tile batch-norm partial sums.
+#include "common.cuh"
+using namespace iea;
+
+namespace {
+
+struct Geo {
+  int64_t M;       // output rows = n*h*w
+  int K;           // cin*taps
+  int hs, ws;      // stored spatial dims of x
+};
+
+__host__ __device__ inline Geo make_geo(const iea_conv_desc& d) {
+  Geo g;
+  g.M = d.n * (int64_t)d.h * d.w;
+  g.K = d.cin * d.ksize * d.ksize;
+  g.hs = d.in_mode == IEA_IN_UP2 ? d.h / 2 : (d.in_mode == IEA_IN_POOL2 ? d.h * 2 : d.h);
+  g.ws = d.in_mode == IEA_IN_UP2 ? d.w / 2 : (d.in_mode == IEA_IN_POOL2 ? d.w * 2 : d.w);
+  return g;
+}
+
+// transformed input element T(x)[n, ih, iw, ci] at conv resolution (ih, iw may be out of range -> 0)
+__device__ __forceinline__ float load_t(const iea_conv_desc& d, const Geo& g, int64_t n, int ih, int iw, int ci) {
+  if ((unsigned)ih >= (unsigned)d.h || (unsigned)iw >= (unsigned)d.w) return 0.f;
+  float sc = 1.f, sh = 0.f;
+  if (d.in_scale) { int64_t si = (d.in_bcast ? 0 : n * d.cin) + ci; sc = d.in_scale[si]; sh = d.in_shift[si]; }
+  if (d.in_mode == IEA_IN_POOL2) {
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        float v = ld_act(d.x, d.x_dtype, ((n * g.hs + 2 * ih + a) * (int64_t)g.ws + 2 * iw + b) * d.x_ld + ci);
+        v = fmaf(v, sc, sh);
+        if (d.in_relu) v = fmaxf(v, 0.f);
+        acc += v;
+      }
+    return 0.25f * acc;
+  }
+  int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
+  float v = ld_act(d.x, d.x_dtype, ((n * g.hs + (ih >> sh_)) * (int64_t)g.ws + (iw >> sh_)) * d.x_ld + ci);
+  v = fmaf(v, sc, sh);
+  if (d.in_relu) v = fmaxf(v, 0.f);
+  return v;
+}
+
+__device__ __forceinline__ float load_res(const iea_conv_desc& d, int64_t n, int oh, int ow, int c) {
+  if (d.res_mode == IEA_IN_UP2) {
+    int hs = d.h / 2, ws = d.w / 2;
+    return ld_act(d.res, d.res_dtype, ((n * hs + (oh >> 1)) * (int64_t)ws + (ow >> 1)) * d.res_ld + c);
+  }
+  if (d.res_mode == IEA_IN_POOL2) {
+    int hs = d.h * 2, ws = d.w * 2;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+        acc += ld_act(d.res, d.res_dtype, ((n * hs + 2 * oh + a) * (int64_t)ws + 2 * ow + b) * d.res_ld + c);
+    return 0.25f * acc;
+  }
+  return ld_act(d.res, d.res_dtype, ((n * d.h + oh) * (int64_t)d.w + ow) * d.res_ld + c);
+}
+
+constexpr int BM = 128, BN = 32, BK = 16;
+
+__global__ void __launch_bounds__(256) conv_fprop_generic(const iea_conv_desc d, const Geo g) {
+  __shared__ __align__(16) float As[BK][BM];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int c0 = blockIdx.y * BN;
+  // A loader: fixed row per thread
+  const int lrow = tid & (BM - 1), lk0 = (tid >> 7) * 8;
+  const int64_t lm = m0 + lrow;
+  const bool lvalid = lm < g.M;
+  int l_ow = 0, l_oh = 0;
+  int64_t l_n = 0;
+  if (lvalid) { l_ow = lm % d.w; int64_t t = lm / d.w; l_oh = t % d.h; l_n = t / d.h; }
+  const int tx = tid & 7, ty = tid >> 3;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int k = k0 + lk0 + j;
+      float v = 0.f;
+      if (lvalid && k < g.K) {
+        int tap = k / d.cin, ci = k - tap * d.cin;
+        int ih = l_oh, iw = l_ow;
+        if (d.ksize == 3) { ih += tap / 3 - 1; iw += tap % 3 - 1; }
+        v = load_t(d, g, l_n, ih, iw, ci);
+      }
+      As[lk0 + j][lrow] = v;
+    }
+    for (int e = tid; e < BK * BN; e += 256) {
+      int kk = e & (BK - 1), cc = e >> 4;
+      int k = k0 + kk, co = c0 + cc;
+      float v = 0.f;
+      if (k < g.K && co < d.cout) v = ld_act(d.wpack, d.w_dtype, (int64_t)co * g.K + k);
+      Bs[kk][cc] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // epilogue
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+    int ow = m % d.w; int64_t t = m / d.w; int oh = t % d.h; int64_t n = t / d.h;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = c0 + tx * 4 + j;
+      if (c >= d.cout) continue;
+      float v = acc[i][j];
+      if (d.out_scale) v *= d.out_scale[d.out_scale_stride ? c : 0];
+      if (d.bias) v += d.bias[c];
+      if (d.res && c < d.res_c) v += load_res(d, n, oh, ow, c);
+      if (d.acc_c0 >= 0 && c >= d.acc_c0) v += ld_act(d.y, d.y_dtype, m * d.y_ld + c);
+      if (d.act == IEA_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (d.act == IEA_ACT_TANH) v = tanhf(v);
+      st_act(d.y, d.y_dtype, m * d.y_ld + c, v);
+      v = round_act(d.y_dtype, v);
+      s1[j] += v;
+      s2[j] = fmaf(v, v, s2[j]);
+    }
+  }
+  if (d.stats) {  // deterministic per-tile column sums (re-using As as scratch)
+    float* r1 = &As[0][0];          // [32 ty][32 cols]
+    float* r2 = r1 + 32 * 32;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { r1[ty * 32 + tx * 4 + j] = s1[j]; r2[ty * 32 + tx * 4 + j] = s2[j]; }
+    __syncthreads();
+    if (tid < 64) {
+      int col = tid & 31, which = tid >> 5;
+      const float* r = which ? r2 : r1;
+      float a = 0.f;
+      for (int y = 0; y < 32; ++y) a += r[y * 32 + col];
+      int c = c0 + col;
+      if (c < d.cout) d.stats[((int64_t)blockIdx.x * d.cout + c) * 2 + which] = a;
+    }
+  }
+}
+
+// ---------------- weight gradient ----------------
+constexpr int WM = 32;  // rows per step
+__global__ void __launch_bounds__(256) conv_wgrad_generic(const iea_conv_desc d, const Geo g, const void* gr,
+                                                          int g_dtype, int g_ld, float* gpart, int64_t rows_per_split) {
+  __shared__ float Gs[WM][33];
+  __shared__ float As[WM][33];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32, split = blockIdx.z;
+  const int64_t mb = (int64_t)split * rows_per_split;
+  int64_t me = mb + rows_per_split;
+  if (me > g.M) me = g.M;
+  const int tk = tid & 15, tc = tid >> 4;
+  float acc[2][2] = {{0, 0}, {0, 0}};
+  const int lrow = tid >> 3, lq = (tid & 7) * 4;
+  for (int64_t ms = mb; ms < me; ms += WM) {
+    int64_t m = ms + lrow;
+    bool valid = m < me;
+    int ow = 0, oh = 0; int64_t n = 0;
+    if (valid) { ow = m % d.w; int64_t t = m / d.w; oh = t % d.h; n = t / d.h; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = k0 + lq + j;
+      float v = 0.f;
+      if (valid && k < g.K) {
+        int tap = k / d.cin, ci = k - tap * d.cin;
+        int ih = oh, iw = ow;
+        if (d.ksize == 3) { ih += tap / 3 - 1; iw += tap % 3 - 1; }
+        v = load_t(d, g, n, ih, iw, ci);
+      }
+      As[lrow][lq + j] = v;
+      int c = c0 + lq + j;
+      Gs[lrow][lq + j] = (valid && c < d.cout) ? ld_act(gr, g_dtype, m * g_ld + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < WM; ++r) {
+      float g0 = Gs[r][tc * 2], g1 = Gs[r][tc * 2 + 1], a0 = As[r][tk * 2], a1 = As[r][tk * 2 + 1];
+      acc[0][0] = fmaf(g0, a0, acc[0][0]); acc[0][1] = fmaf(g0, a1, acc[0][1]);
+      acc[1][0] = fmaf(g1, a0, acc[1][0]); acc[1][1] = fmaf(g1, a1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+  float* out = gpart + (int64_t)split * d.cout * g.K;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int c = c0 + tc * 2 + i, k = k0 + tk * 2 + j;
+      if (c < d.cout && k < g.K) out[(int64_t)c * g.K + k] = acc[i][j];
+    }
+}
+
+// ---------------- backward of the prologue T ----------------
+// grid (n, channel chunks); block = CB channels x (256/CB) pixel lanes.
+__global__ void __launch_bounds__(256) conv_input_bwd_kernel(const iea_conv_desc d, const Geo g, const void* da,
+                                                            int da_dtype, void* dx, int dx_dtype, int dx_ld,
+                                                            float beta, float* dscale, float* dshift, int cb) {
+  __shared__ float r1[256], r2[256];
+  const int64_t n = blockIdx.x;
+  const int lanes = 256 / cb;
+  const int cl = threadIdx.x % cb, pl = threadIdx.x / cb;
+  const int c = blockIdx.y * cb + cl;
+  float a_s = 0.f, a_h = 0.f;
+  if (c < d.cin) {
+    float sc = 1.f, sh = 0.f;
+    if (d.in_scale) { int64_t si = (d.in_bcast ? 0 : n * d.cin) + c; sc = d.in_scale[si]; sh = d.in_shift[si]; }
+    const int64_t npx = (int64_t)g.hs * g.ws;
+    for (int64_t p = pl; p < npx; p += lanes) {
+      int xw = p % g.ws, xh = p / g.ws;
+      float xv = ld_act(d.x, d.x_dtype, (n * npx + p) * d.x_ld + c);
+      float gsum;
+      if (d.in_mode == IEA_IN_UP2) {
+        gsum = 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            gsum += ld_act(da, da_dtype, ((n * d.h + 2 * xh + a) * (int64_t)d.w + 2 * xw + b) * d.cin + c);
+      } else if (d.in_mode == IEA_IN_POOL2) {
+        gsum = 0.25f * ld_act(da, da_dtype, ((n * d.h + (xh >> 1)) * (int64_t)d.w + (xw >> 1)) * d.cin + c);
+      } else {
+        gsum = ld_act(da, da_dtype, (n * npx + p) * d.cin + c);
+      }
+      float pre = fmaf(xv, sc, sh);
+      if (d.in_relu && pre <= 0.f) gsum = 0.f;
+      a_h += gsum;
+      a_s = fmaf(gsum, xv, a_s);
+      if (dx) {
+        float v = gsum * sc;
+        int64_t o = (n * npx + p) * dx_ld + c;
+        if (beta != 0.f) v = fmaf(beta, ld_act(dx, dx_dtype, o), v);
+        st_act(dx, dx_dtype, o, v);
+      }
+    }
+  }
+  if (dscale) {
+    r1[threadIdx.x] = a_s; r2[threadIdx.x] = a_h;
+    __syncthreads();
+    if (pl == 0 && c < d.cin) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int l = 0; l < lanes; ++l) { t1 += r1[l * cb + cl]; t2 += r2[l * cb + cl]; }
+      dscale[n * d.cin + c] = t1;
+      dshift[n * d.cin + c] = t2;
+    }
+  }
+}
+
+// g = dy*act' + ds1 + 2*y*ds2
+__global__ void conv_out_bwd_kernel(const void* dy, int dy_dtype, int dy_ld, const void* y, int y_dtype, int y_ld,
+                                    int act, const float* ds1, const float* ds2, int64_t rows, int rows_per_event,
+                                    int c, void* gout, int g_dtype) {
+  const int64_t total = rows * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = i / c; int cc = i - m * c;
+    float v = ld_act(dy, dy_dtype, m * dy_ld + cc);
+    float yv = (act == IEA_ACT_TANH || ds2) ? ld_act(y, y_dtype, m * y_ld + cc) : 0.f;
+    if (act == IEA_ACT_TANH) v *= (1.f - yv * yv);
+    if (ds1) {
+      int64_t e = m / rows_per_event;
+      v += ds1[e * c + cc] + 2.f * yv * ds2[e * c + cc];
+    }
+    st_act(gout, g_dtype, i, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_part(const void* g, int g_dtype, int g_ld, int64_t rows, int c,
+                                                   float* part, int64_t rows_per_block) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block; if (r1 > rows) r1 = rows;
+  __shared__ float red[256];
+  const int cb = c < 256 ? c : 256;          // channels per pass
+  const int lanes = 256 / cb > 0 ? 256 / cb : 1;
+  for (int cbase = 0; cbase < c; cbase += cb) {
+    int cl = threadIdx.x % cb, pl = threadIdx.x / cb;
+    int cc = cbase + cl;
+    float a = 0.f;
+    if (pl < lanes && cc < c)
+      for (int64_t m = r0 + pl; m < r1; m += lanes) a += ld_act(g, g_dtype, m * g_ld + cc);
+    red[threadIdx.x] = a;
+    __syncthreads();
+    if (pl == 0 && cc < c) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += red[l * cb + cl];
+      part[(int64_t)blockIdx.x * c + cc] = t;
+    }
+    __syncthreads();
+  }
+}
+__global__ void colsum_final(const float* part, int blocks, int c, float* out, float beta) {
+  int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc >= c) return;
+  float t = 0.f;
+  for (int b = 0; b < blocks; ++b) t += part[(int64_t)b * c + cc];
+  out[cc] = beta != 0.f ? fmaf(beta, out[cc], t) : t;
+}
+
+__global__ void residual_bwd_kernel(const void* g, int g_dtype, int g_ld, int64_t n, int h, int w, int res_c,
+                                    int res_mode, void* dres, int dres_dtype, int dres_ld, int dres_c, float beta) {
+  const int hs = res_mode == IEA_IN_UP2 ? h / 2 : (res_mode == IEA_IN_POOL2 ? h * 2 : h);
+  const int ws = res_mode == IEA_IN_UP2 ? w / 2 : (res_mode == IEA_IN_POOL2 ? w * 2 : w);
+  const int64_t total = n * hs * (int64_t)ws * dres_c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % dres_c; int64_t p = i / dres_c;
+    int xw = p % ws; int64_t t = p / ws; int xh = t % hs; int64_t nn = t / hs;
+    float v = 0.f;
+    if (c < res_c) {
+      if (res_mode == IEA_IN_UP2) {
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b)
+            v += ld_act(g, g_dtype, ((nn * h + 2 * xh + a) * (int64_t)w + 2 * xw + b) * g_ld + c);
+      } else if (res_mode == IEA_IN_POOL2) {
+        v = 0.25f * ld_act(g, g_dtype, ((nn * h + (xh >> 1)) * (int64_t)w + (xw >> 1)) * g_ld + c);
+      } else {
+        v = ld_act(g, g_dtype, p * g_ld + c);
+      }
+    }
+    int64_t o = p * dres_ld + c;
+    if (beta != 0.f) v = fmaf(beta, ld_act(dres, dres_dtype, o), v);
+    st_act(dres, dres_dtype, o, v);
+  }
+}
+
+inline int ew_blocks(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace
+
+int iea_conv_fprop_generic(const iea_conv_desc* d, cudaStream_t s) {
+  Geo g = make_geo(*d);
+  dim3 grid(cdiv(g.M, BM), cdiv(d->cout, BN));
+  conv_fprop_generic<<<grid, 256, 0, s>>>(*d, g);
+  return check_launch("iea_conv_fprop(generic)");
+}
+
+extern "C" int iea_conv_wgrad(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* gpart,
+                              int nsplit, iea_stream_t stream) {
+  IEA_CHECK_ARG(nsplit >= 1, "iea_conv_wgrad: nsplit must be >= 1");
+  Geo geo = make_geo(*d);
+  int64_t rps = (geo.M + nsplit - 1) / nsplit;
+  rps = (rps + WM - 1) / WM * WM;
+  dim3 grid(cdiv(geo.K, 32), cdiv(d->cout, 32), nsplit);
+  conv_wgrad_generic<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, geo, g, g_dtype, g_ld, gpart, rps);
+  return check_launch("iea_conv_wgrad");
+}
+
+extern "C" int iea_conv_input_bwd(const iea_conv_desc* d, const void* da, int da_dtype, void* dx, int dx_dtype,
+                                  int dx_ld, float beta, float* dscale, float* dshift, iea_stream_t stream) {
+  Geo g = make_geo(*d);
+  int cb = 1;
+  while (cb < d->cin && cb < 32) cb <<= 1;
+  dim3 grid((unsigned)d->n, cdiv(d->cin, cb));
+  conv_input_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, g, da, da_dtype, dx, dx_dtype, dx_ld, beta,
+                                                                 dscale, dshift, cb);
+  return check_launch("iea_conv_input_bwd");
+}
+
+extern "C" int iea_conv_out_bwd(const void* dy, int dy_dtype, int dy_ld, const void* y, int y_dtype, int y_ld,
+                                int act, const float* ds1, const float* ds2, int64_t rows, int rows_per_event,
+                                int c, void* g, int g_dtype, iea_stream_t stream) {
+  conv_out_bwd_kernel<<<ew_blocks(rows * c), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, dy_ld, y, y_dtype, y_ld,
+                                                                             act, ds1, ds2, rows, rows_per_event, c,
+                                                                             g, g_dtype);
+  return check_launch("iea_conv_out_bwd");
+}
+
+extern "C" int iea_colsum(const void* g, int g_dtype, int g_ld, int64_t rows, int c, float* out, float beta,
+                          float* scratch, iea_stream_t stream) {
+  int blocks = (int)((rows + 511) / 512);
+  if (blocks > 296) blocks = 296;
+  if (blocks < 1) blocks = 1;
+  int64_t rpb = (rows + blocks - 1) / blocks;
+  colsum_part<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, g_dtype, g_ld, rows, c, scratch, rpb);
+  colsum_final<<<cdiv(c, 128), 128, 0, (cudaStream_t)stream>>>(scratch, blocks, c, out, beta);
+  return check_launch("iea_colsum");
+}
+
+extern "C" int iea_residual_bwd(const void* g, int g_dtype, int g_ld, int64_t n, int h, int w, int res_c,
+                                int res_mode, void* dres, int dres_dtype, int dres_ld, int dres_c, float beta,
+                                iea_stream_t stream) {
+  int hs = res_mode == IEA_IN_UP2 ? h / 2 : (res_mode == IEA_IN_POOL2 ? h * 2 : h);
+  int ws = res_mode == IEA_IN_UP2 ? w / 2 : (res_mode == IEA_IN_POOL2 ? w * 2 : w);
+  residual_bwd_kernel<<<ew_blocks(n * hs * (int64_t)ws * dres_c), 256, 0, (cudaStream_t)stream>>>(
+      g, g_dtype, g_ld, n, h, w, res_c, res_mode, dres, dres_dtype, dres_ld, dres_c, beta);
+  return check_launch("iea_residual_bwd");
+}

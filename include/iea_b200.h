@@ -1,0 +1,248 @@
+/* iea_b200.h -- C ABI of libiea_sm100.so, the sm_100a (B200) implementation of the
+ * IEA-GAN Generator/Discriminator hot path.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success and a negative code on failure; the
+ *     message is available from iea_last_error() (thread local).
+ *   - all pointers are DEVICE pointers unless a comment says host; the library never
+ *     allocates, frees or synchronises: the caller owns every buffer (inputs, outputs,
+ *     saved tensors and scratch) and passes the CUDA stream to enqueue on.
+ *   - activations are NHWC ([n][h][w][c], channel stride 1, pixel stride `ld`), element
+ *     type given by an iea_dtype code; parameters stay fp32 in the reference's layout.
+ *   - rows of a batch are grouped by event: 40 consecutive images (model.py:466).
+ *
+ * Each declaration cites the reference interface (file:line in Baran-phys/IEA-GAN) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef IEA_B200_H
+#define IEA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* iea_stream_t; /* cudaStream_t */
+
+enum iea_dtype { IEA_F32 = 0, IEA_BF16 = 1 };
+enum iea_in_mode { IEA_IN_DIRECT = 0, IEA_IN_UP2 = 1, IEA_IN_POOL2 = 2 };
+enum iea_act { IEA_ACT_NONE = 0, IEA_ACT_RELU = 1, IEA_ACT_TANH = 2 };
+enum iea_impl { IEA_IMPL_AUTO = 0, IEA_IMPL_GENERIC = 1, IEA_IMPL_TCGEN05 = 2 };
+
+/* ---- library ------------------------------------------------------------------ */
+int iea_version(void);
+const char* iea_last_error(void);
+/* fails unless the current device is compute capability 10.x (no fallback path) */
+int iea_require_sm100(int device);
+int iea_sm_count(int device);
+
+/* ---- spectral norm: layers.py:89-111 power_iteration, layers.py:151-165 SN.W_ ----
+ * One grouped call runs the power iteration of EVERY listed layer (v = norm(uW),
+ * u' = norm(vW^T), sigma = |vW^T|) and repacks the fp32 master weight into the
+ * activation dtype in the two layouts the conv kernels consume.  W/sigma is never
+ * materialised: 1/sigma is applied in the conv epilogue. */
+typedef struct {
+  const float* w;        /* [rows][cin][taps] fp32 master weight (taps = k*k, cols = cin*taps) */
+  const float* u_in;     /* [rows] stored u0 */
+  float* u_out;          /* [rows] u' (u0 itself when training, scratch otherwise) */
+  float* v_out;          /* [cols] v, saved for the backward rank-1 correction */
+  float* sigma_out;      /* [1] sv0 when training, scratch otherwise; may be NULL */
+  float* inv_sigma_out;  /* [1] 1/sigma (1.0 when !spectral) */
+  float* colscale_out;   /* optional [colscale_n]: filled with 1/sigma (grouped ccbn GEMM) */
+  void* pack_fprop;      /* optional [rows][taps][cin] in pack_dtype */
+  void* pack_dgrad;      /* optional [cin][taps, spatially flipped][pack_dgrad_ld >= rows] in pack_dtype */
+  int32_t rows, cin, taps, colscale_n;
+  int32_t pack_dgrad_ld; /* row stride of pack_dgrad (lets several layers share one dgrad matrix) */
+  int32_t pack_dtype;    /* iea_dtype */
+  int32_t spectral;      /* 0: plain layer, only repack */
+  float eps;
+  int32_t chunk0;        /* first entry of this layer in the chunk table */
+  int32_t nchunks;
+  int64_t scratch_off;   /* float offset of this layer's scratch (partials + t) */
+} iea_sn_layer;
+/* chunk table: int32 triples (layer, row_begin, row_end); scratch: fp32 */
+int iea_sn_power_iter(const iea_sn_layer* layers_dev, int n_layers, const int32_t* chunks_dev,
+                      int n_chunks, float* scratch, int max_cols, iea_stream_t stream);
+
+/* backward of W/sigma: dW = G/sigma - (<G,W>/sigma^2) u'^T v, where
+ * G = sum over `nsplit` wgrad partials [nsplit][rows][taps][cin] (fp32).  Writes (beta=0) or
+ * accumulates (beta=1) dW in the master layout [rows][cin][taps]. */
+int iea_sn_weight_bwd(const float* gpart, int nsplit, const float* w, const float* u, const float* v,
+                      const float* inv_sigma, int spectral, float* dw, float beta, int rows, int cin,
+                      int taps, float* scratch /* >= 2 + 2*gridcap floats */, iea_stream_t stream);
+
+/* ---- fused convolution / linear: layers.py:197-206 SNConv2d.forward, :223-224 SNLinear ----
+ * y = act( conv_k(T(x), Wpack) * out_scale + bias + residual ), with
+ *   T(x) = [avgpool2 | nearest-up2]( relu?( x * in_scale[n][c] + in_shift[n][c] ) )
+ * (T fuses ccbn/bn apply + ReLU + F.interpolate / AvgPool2d: model.py:56-70, 545-556) and an
+ * optional per-128-row-tile (sum, sum of squares) of y for the next batch-norm. A linear
+ * layer is the 1x1 case with h = w = 1.  The same kernel is the data-gradient when given
+ * pack_dgrad weights. */
+typedef struct {
+  int64_t n; int32_t h, w;             /* output (= conv input after T) geometry */
+  int32_t cin, cout, ksize;            /* ksize 1 or 3, stride 1, padding ksize/2 */
+  const void* x; int32_t x_dtype, x_ld, in_mode, in_relu;
+  const float* in_scale; const float* in_shift;   /* [n][cin] ([cin] when in_bcast) or NULL */
+  int32_t in_bcast;
+  const void* wpack; int32_t w_dtype;  /* [cout][taps][cin] */
+  const float* out_scale; int32_t out_scale_stride; /* 0: scalar, 1: per out channel; NULL: 1 */
+  const float* bias;                   /* [cout] or NULL */
+  const void* res; int32_t res_dtype, res_ld, res_mode, res_c; /* residual for channels < res_c */
+  int32_t acc_c0;                      /* channels >= acc_c0 add the existing y value; <0: off */
+  void* y; int32_t y_dtype, y_ld, act;
+  float* stats;                        /* [ceil(M/128)][cout][2] or NULL, M = n*h*w */
+  int32_t impl;                        /* iea_impl */
+} iea_conv_desc;
+int iea_conv_fprop(const iea_conv_desc* d /* host */, iea_stream_t stream);
+/* 1 if the tcgen05 path accepts this descriptor */
+int iea_conv_tc_supported(const iea_conv_desc* d /* host */);
+
+/* weight gradient: gpart[s][cout][taps][cin] = sum over the rows of split s of g[m][co]*T(x)[m][k];
+ * g is the gradient at the conv accumulator (dtype g_dtype, pixel stride g_ld). */
+int iea_conv_wgrad(const iea_conv_desc* d /* host; x/T fields and geometry are used */, const void* g,
+                   int g_dtype, int g_ld, float* gpart, int nsplit, iea_stream_t stream);
+
+/* backward of T: da [n][h][w][cin] (at conv resolution) -> dx at x's resolution and the
+ * per-(n,c) reductions dscale = sum da*relu'*x, dshift = sum da*relu'.  beta=1 accumulates dx. */
+int iea_conv_input_bwd(const iea_conv_desc* d /* host */, const void* da, int da_dtype, void* dx,
+                       int dx_dtype, int dx_ld, float beta, float* dscale, float* dshift,
+                       iea_stream_t stream);
+
+/* g = (dy [* (1 - y^2) if act == TANH]) + ds1[e][c] + 2*y*ds2[e][c]   (batch-norm statistics path) */
+int iea_conv_out_bwd(const void* dy, int dy_dtype, int dy_ld, const void* y, int y_dtype, int y_ld,
+                     int act, const float* ds1, const float* ds2, int64_t rows, int rows_per_event,
+                     int c, void* g, int g_dtype, iea_stream_t stream);
+
+/* out[c] = sum_m g[m][c] (bias gradient); scratch >= blocks*c floats */
+int iea_colsum(const void* g, int g_dtype, int g_ld, int64_t rows, int c, float* out, float beta,
+               float* scratch, iea_stream_t stream);
+
+/* residual gradient: dres[n][h'][w'][c<res_c] (+)= adjoint of the epilogue's residual read */
+int iea_residual_bwd(const void* g, int g_dtype, int g_ld, int64_t n, int h, int w, int res_c,
+                     int res_mode, void* dres, int dres_dtype, int dres_ld, int dres_c, float beta,
+                     iea_stream_t stream);
+
+/* ---- batch norm: layers.py:656-689 ccbn.forward, :728-742 bn.forward --------------- */
+/* stand-alone statistics partials: [events][tiles][c][2] */
+int iea_bn_stats(const void* x, int x_dtype, int x_ld, int64_t rows, int rows_per_event, int c,
+                 int tiles_per_event, float* partials, iea_stream_t stream);
+/* partials -> batch mean / rstd per (event, c) (biased variance), running-stat update
+ * (momentum, unbiased variance) when training; eval uses the stored statistics.
+ * scale[n][c] = rstd*(gain_add + gain[n*gain_ld + c]); shift = bias - mean*scale. */
+int iea_bn_finalize(const float* partials, int events, int tiles_per_event, int64_t count_per_event,
+                    int imgs_per_event, int c, const float* gain, int64_t gain_ld, float gain_add,
+                    const float* bias, int64_t bias_ld, float* stored_mean, float* stored_var,
+                    int training, float momentum, float eps, float* mean_out, float* rstd_out,
+                    float* scale, float* shift, iea_stream_t stream);
+/* backward: (dscale, dshift)[n][c] -> dgain[n][c], dbias[n][c] (pixel-stride ld, beta accumulate)
+ * and the statistics gradients ds1, ds2 [events][c] consumed by iea_conv_out_bwd. */
+int iea_bn_finalize_bwd(const float* dscale, const float* dshift, const float* scale,
+                        const float* mean, const float* rstd, int events, int imgs_per_event,
+                        int64_t count_per_event, int c, const float* gain, int64_t gain_ld,
+                        float gain_add, float* dgain, int64_t dgain_ld, float* dbias,
+                        int64_t dbias_ld, int reduce_over_n, int training, float* ds1, float* ds2,
+                        iea_stream_t stream);
+/* y = [relu](x*scale[n][c] + shift[n][c]) : stand-alone apply for the module-level API */
+int iea_affine_act(const void* x, int x_dtype, const float* scale, const float* shift, int64_t n,
+                   int64_t hw, int c, int relu, void* y, int y_dtype, iea_stream_t stream);
+
+/* ---- layout / elementwise helpers ------------------------------------------------- */
+/* NCHW (src_dtype) <-> NHWC (dst_dtype) */
+int iea_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, int c,
+                     int64_t hw, iea_stream_t stream);
+int iea_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, int c,
+                     int64_t hw, iea_stream_t stream);
+/* y = alpha*a + beta*b (b may be NULL); all contiguous with count elements */
+int iea_axpby(const void* a, int a_dtype, float alpha, const void* b, int b_dtype, float beta,
+              void* y, int y_dtype, int64_t count, iea_stream_t stream);
+/* y = gamma[0]*o + x (layers.py:300); backward: dgamma = sum(dy*o), do = gamma*dy */
+int iea_gamma_residual(const void* o, const void* x, int dtype, const float* gamma, void* y,
+                       int64_t count, iea_stream_t stream);
+int iea_gamma_residual_bwd(const void* dy, const void* o, int dtype, const float* gamma, void* d_o,
+                           float* dgamma, float* scratch, int64_t count, iea_stream_t stream);
+/* F.embedding(idx, W*scale): layers.py:259, model.py:462 */
+int iea_embedding_fwd(const int64_t* idx, const float* w, const float* scale, int64_t n, int dim,
+                      float* out, iea_stream_t stream);
+int iea_embedding_bwd(const int64_t* idx, const float* dout, const float* scale, int64_t n, int dim,
+                      int rows, float* dw /* [rows][dim], zeroed inside */, iea_stream_t stream);
+/* torch.sum(relu(h), [2,3]): model.py:912 */
+int iea_relu_sumpool_fwd(const void* x, int x_dtype, int64_t n, int64_t hw, int c, float* out,
+                         iea_stream_t stream);
+int iea_relu_sumpool_bwd(const void* x, int x_dtype, const float* dout, int64_t n, int64_t hw, int c,
+                         void* dx, int dx_dtype, iea_stream_t stream);
+/* F.max_pool2d(x, 2): layers.py:286-287 (index saved as uint8 0..3) */
+int iea_maxpool2_fwd(const void* x, int dtype, int64_t n, int h, int w, int c, void* y, uint8_t* idx,
+                     iea_stream_t stream);
+int iea_maxpool2_bwd(const void* dy, int dtype, const uint8_t* idx, int64_t n, int h, int w, int c,
+                     void* dx, iea_stream_t stream);
+/* nn.LayerNorm over the last dim (RRM.py:94-95,118; model.py:798) fp32 rows */
+int iea_layernorm_fwd(const float* x, const float* g, const float* b, int64_t rows, int dim, float eps,
+                      float* y, float* mean, float* rstd, iea_stream_t stream);
+int iea_layernorm_bwd(const float* dy, const float* x, const float* g, const float* mean,
+                      const float* rstd, int64_t rows, int dim, float* dx, float* dg_part,
+                      float* db_part, int nparts, iea_stream_t stream);
+/* F.normalize(x, dim=1): model.py:934-935 */
+int iea_l2norm_fwd(const float* x, int64_t rows, int dim, float eps, float* y, float* norm,
+                   iea_stream_t stream);
+int iea_l2norm_bwd(const float* dy, const float* y, const float* norm, int64_t rows, int dim, float eps,
+                   float* dx, iea_stream_t stream);
+
+/* ---- RRM attention: RRM.py:10-16 scaled_dot_product on the per-head-interleaved qkv ---- */
+/* qkv [events][40][heads][3*d] fp32 -> val [events][40][heads*d]; att [events][heads][40][40] saved */
+int iea_mha_fwd(const float* qkv, int events, int seq, int heads, int d, float* val, float* att,
+                iea_stream_t stream);
+int iea_mha_bwd(const float* dval, const float* qkv, const float* att, int events, int seq, int heads,
+                int d, float* dqkv, iea_stream_t stream);
+
+/* ---- BigGAN self-attention core: layers.py:289-299 (softmax(theta^T phi), o = g beta^T) ---- */
+/* theta [n][hw][ck], phi [n][hw/4][ck], g [n][hw/4][cv] -> o [n][hw][cv]; lse [n][hw] saved */
+int iea_attn_fwd(const void* theta, const void* phi, const void* g, int dtype, int64_t n, int hw,
+                 int hwk, int ck, int cv, void* o, float* lse, iea_stream_t stream);
+int iea_attn_bwd(const void* d_o, const void* theta, const void* phi, const void* g, const void* o,
+                 const float* lse, int dtype, int64_t n, int hw, int hwk, int ck, int cv,
+                 void* dtheta, void* dphi, void* dg, float* dq_scratch /* [n][hw] */,
+                 iea_stream_t stream);
+
+/* ---- DiffAugment: diff_aug.py:23-102, closed form of SURVEY.md Appendix B.9 ---------- */
+typedef struct {
+  const float* brightness; const float* contrast;     /* [n] raw U(0,1) draws or NULL */
+  const int64_t* tx; const int64_t* ty;               /* [n] or NULL */
+  const int64_t* ox; const int64_t* oy; int32_t cut_h, cut_w; /* [n] or NULL */
+} iea_aug_draws;
+int iea_diffaug_fwd(const float* x, const iea_aug_draws* d /* host */, int64_t n, int h, int w, float* y,
+                    float* mean_scratch /* [n] */, iea_stream_t stream);
+int iea_diffaug_bwd(const float* dy, const iea_aug_draws* d /* host */, int64_t n, int h, int w,
+                    float* dx, float* mean_scratch /* [n] */, iea_stream_t stream);
+
+/* ---- losses: loss.py:8-9, 14-27, 30-38, 79-132 (per event of `seq` rows, then averaged) ---- */
+/* out[0] = mean relu(1 - real), out[1] = mean relu(1 + fake) */
+int iea_loss_hinge_dis(const float* fake, const float* real, int64_t n, float* out, iea_stream_t stream);
+int iea_loss_hinge_dis_bwd(const float* fake, const float* real, const float* dout /* [2] */, int64_t n,
+                           float* dfake, float* dreal, iea_stream_t stream);
+/* out[0] = scale * mean(x) (loss_hinge_gen: scale = -1) and its backward dx[i] = dout*scale/n */
+int iea_loss_mean(const float* x, int64_t n, float scale, float* out, iea_stream_t stream);
+int iea_loss_mean_bwd(const float* dout, int64_t n, float scale, float* dx, iea_stream_t stream);
+int iea_loss_contrastive_fwd(const float* embed, const float* proxy, int events, int seq, int dim,
+                             float temperature, float margin, float* loss, float* saved /* events*(2*seq*seq+4*seq+1) */,
+                             iea_stream_t stream);
+int iea_loss_contrastive_bwd(const float* embed, const float* proxy, const float* saved,
+                             const float* dloss, int events, int seq, int dim, float temperature,
+                             float* dembed, float* dproxy, iea_stream_t stream);
+int iea_loss_iea_fwd(const float* kf, const float* kr, int events, int seq, int dim, float* loss,
+                     float* saved /* events*(seq*seq+1) */, iea_stream_t stream);
+int iea_loss_iea_bwd(const float* kf, const float* saved, const float* dloss, int events, int seq,
+                     int dim, float* dkf, iea_stream_t stream);
+int iea_loss_unif_fwd(const float* x, int events, int seq, int dim, float t, float* loss,
+                      float* saved /* events*(seq*seq+2) */, iea_stream_t stream);
+int iea_loss_unif_bwd(const float* x, const float* saved, const float* dloss, int events, int seq,
+                      int dim, float t, float* dx, iea_stream_t stream);
+
+/* ---- sampling post-process: model.py:1139-1147 (7-ADU cut, 256^x - 1, clamp, crop 3 rows) ---- */
+int iea_adu_postprocess(const float* img, int64_t n, int h, int w, float* out /* [n][h-6][w] */,
+                        iea_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IEA_B200_H */

@@ -1,0 +1,225 @@
+"""GPU parity tests of the individual kernels against plain torch fp32 (through the C ABI).
+Tolerances: fp32 kernels 1e-4 relative L2 (different summation order); bf16 storage 1.5e-2."""
+import ctypes as C
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from iea_gan_b200 import engine, _lib
+    _lib.lib()
+    return engine
+
+
+class _Mod(torch.nn.Module):
+    pass
+
+
+def make_sn_conv(cin, cout, k, dev, bias=True):
+    from iea_gan_b200 import sn_layers as SL
+    m = SL.SNConv2d(cin, cout, k, padding=k // 2, bias=bias, eps=1e-6).to(dev)
+    return m
+
+
+@pytest.mark.parametrize("cin,cout,k", [(16, 32, 3), (64, 16, 1), (1, 32, 3), (32, 1, 3), (12, 20, 3)])
+def test_sn_power_iter_and_pack(eng, cin, cout, k):
+    dev = "cuda"
+    torch.manual_seed(1)
+    m = make_sn_conv(cin, cout, k, dev)
+    grp = eng.SNGroup()
+    l = grp.add(m, torch.float32)
+    W = m.weight.detach().reshape(cout, -1).clone()
+    u0 = m.u0.clone()
+    v = F.normalize(u0 @ W, eps=1e-6)
+    un = F.normalize(v @ W.t(), eps=1e-6)
+    sig = float(((v @ W.t()) @ un.t()).squeeze())
+    m.train()
+    grp.run(True, True)
+    torch.cuda.synchronize()
+    assert rel(l.v(), v.view(-1)) < 1e-5
+    assert rel(m.u0, un) < 1e-5
+    assert abs(float(m.sv0) - sig) < 1e-4 * abs(sig)
+    assert abs(float(l.inv_sigma()) - 1 / sig) < 1e-4 / abs(sig)
+    wp = m.weight.detach().permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    assert torch.equal(l.wp, wp)
+    wd = m.weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k, cout)
+    assert torch.equal(l.wd, wd)
+    # eval mode: nothing is written
+    m.eval()
+    ub, sb = m.u0.clone(), m.sv0.clone()
+    grp.run(False, False)
+    torch.cuda.synchronize()
+    assert torch.equal(ub, m.u0) and torch.equal(sb, m.sv0)
+
+
+def _ref_T(x, scale, shift, relu, mode):
+    if scale is not None:
+        x = x * scale[:, :, None, None] + shift[:, :, None, None]
+    if relu:
+        x = F.relu(x)
+    if mode == 1:
+        x = F.interpolate(x, scale_factor=2)
+    elif mode == 2:
+        x = F.avg_pool2d(x, 2)
+    return x
+
+
+@pytest.mark.parametrize("adt", ["fp32", "bf16"])
+@pytest.mark.parametrize("cin,cout,k,mode,relu,aff,resm", [
+    (16, 32, 3, 0, True, True, None), (64, 16, 1, 1, True, True, 1), (32, 48, 3, 2, True, False, 2),
+    (1, 32, 3, 0, False, False, None), (32, 1, 3, 0, True, True, None), (20, 12, 1, 0, False, False, 0)])
+def test_conv_fprop_and_backward(eng, adt, cin, cout, k, mode, relu, aff, resm):
+    """Fused conv forward + every backward product against torch autograd."""
+    from iea_gan_b200 import _lib as L
+    os.environ["IEA_ACT_DTYPE"] = adt
+    os.environ["IEA_CONV_IMPL"] = "generic"
+    try:
+        dev = "cuda"
+        at = eng.act_dtype()
+        torch.manual_seed(2)
+        n, h, w = 40, 8, 12
+        hs, ws = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+        m = make_sn_conv(cin, cout, k, dev)
+        m.train()
+        x = torch.randn(n, cin, hs, ws, device=dev)
+        xq = x.to(at).float()  # what the kernel sees
+        scale = (torch.rand(n, cin, device=dev) + 0.5) if aff else None
+        shift = torch.randn(n, cin, device=dev) * 0.3 if aff else None
+        rc = None
+        if resm is not None:
+            rc = cout if resm != 2 else cout
+            rh, rw = (h // 2, w // 2) if resm == 1 else ((2 * h, 2 * w) if resm == 2 else (h, w))
+            r = torch.randn(n, cout + 4, rh, rw, device=dev)
+            rq = r.to(at).float()
+        # --- torch reference with autograd
+        Wt = m.weight.detach().clone().requires_grad_(True)
+        bt = m.bias.detach().clone().requires_grad_(True)
+        W2 = Wt.reshape(cout, -1)
+        u0 = m.u0.clone()
+        with torch.no_grad():
+            v = F.normalize(u0 @ W2, eps=1e-6)
+            un = F.normalize(v @ W2.t(), eps=1e-6)
+        sig = ((v @ W2.t()) @ un.t()).squeeze()
+        xr = xq.clone().requires_grad_(True)
+        sr = scale.clone().requires_grad_(True) if aff else None
+        hr = shift.clone().requires_grad_(True) if aff else None
+        a = _ref_T(xr, sr, hr, relu, mode)
+        Wq = Wt.detach().to(at).float()  # value the kernel multiplies with; gradient flows to Wt
+        yref = F.conv2d(a, (Wq + (Wt - Wt.detach())) / sig, bt, padding=k // 2)
+        if resm is not None:
+            rr = rq.clone().requires_grad_(True)
+            yref = yref + _ref_T(rr[:, :cout], None, None, False, resm)
+        # --- kernel
+        grp = eng.SNGroup()
+        l = grp.add(m, at)
+        grp.run(True, True)
+        tape = eng.Tape(True)
+        xv = eng.Var(x.permute(0, 2, 3, 1).contiguous().to(at))
+        ss = eng.ScaleShift(scale.contiguous(), shift.contiguous()) if aff else None
+        resv = None
+        if resm is not None:
+            resv = eng.Var(r.permute(0, 2, 3, 1).contiguous().to(at))
+        yv = eng.conv(tape, xv, l, n, h, w, k, bias=m.bias, in_mode=mode, in_relu=relu, ss=ss, res=resv,
+                      res_mode=resm or 0, res_c=cout if resm is not None else 0, stats=True, out_dtype=torch.float32)
+        y = yv.t.permute(0, 3, 1, 2)
+        tol = 2e-5 if adt == "fp32" else 1.5e-2
+        assert rel(y, yref) < tol
+        # epilogue statistics
+        st = yv.t.reshape(-1, cout)
+        part = yv.bn
+        # backward
+        gy = torch.randn_like(yref)
+        yref.backward(gy)
+        yv.g = gy.permute(0, 2, 3, 1).contiguous()
+        tape.backward()
+        torch.cuda.synchronize()
+        btol = 1e-4 if adt == "fp32" else 2.5e-2
+        assert rel(xv.g.float().permute(0, 3, 1, 2), xr.grad) < btol
+        assert rel(tape.pgrads[id(m.weight)], Wt.grad) < btol
+        assert rel(tape.pgrads[id(m.bias)], bt.grad) < btol
+        if aff:
+            assert rel(ss.dscale, sr.grad) < btol
+            assert rel(ss.dshift, hr.grad) < btol
+        if resm is not None:
+            assert rel(resv.g.float().permute(0, 3, 1, 2), rr.grad) < btol
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)
+        os.environ.pop("IEA_CONV_IMPL", None)
+
+
+def test_conv_epilogue_stats(eng):
+    os.environ["IEA_ACT_DTYPE"] = "fp32"
+    try:
+        dev = "cuda"
+        torch.manual_seed(3)
+        n, h, w, cin, cout = 80, 8, 8, 16, 24
+        m = make_sn_conv(cin, cout, 3, dev)
+        grp = eng.SNGroup()
+        l = grp.add(m, torch.float32)
+        grp.run(True, False)
+        x = torch.randn(n, h, w, cin, device=dev)
+        yv = eng.conv(eng.Tape(False), eng.Var(x), l, n, h, w, 3, bias=m.bias, stats=True, out_dtype=torch.float32)
+        part, tiles, count = yv.bn
+        assert count == 40 * h * w and tiles == count // 128
+        y = yv.t.reshape(2, -1, cout)
+        s = part.reshape(2, tiles, cout, 2).sum(1)
+        assert rel(s[..., 0], y.sum(1)) < 1e-5
+        assert rel(s[..., 1], (y * y).sum(1)) < 1e-5
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)
+
+
+def test_layernorm_mha_l2norm(eng):
+    dev = "cuda"
+    torch.manual_seed(4)
+    ln = torch.nn.LayerNorm(128).to(dev)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.normal_()
+    x = torch.randn(80, 128, device=dev)
+    xr = x.clone().requires_grad_(True)
+    yr = ln(xr)
+    tape = eng.Tape(True)
+    xv = eng.Var(x)
+    yv = eng.layernorm(tape, xv, ln)
+    assert rel(yv.t, yr) < 1e-5
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    yv.g = g
+    tape.backward()
+    assert rel(xv.g, xr.grad) < 1e-4
+    assert rel(tape.pgrads[id(ln.weight)], ln.weight.grad) < 1e-4
+    assert rel(tape.pgrads[id(ln.bias)], ln.bias.grad) < 1e-4
+    # per-head interleaved attention (RRM.py:49-53)
+    for heads, d in ((2, 64), (4, 128)):
+        E = 2
+        qkv = torch.randn(E * 40, heads * 3 * d, device=dev)
+        qr = qkv.clone().requires_grad_(True)
+        t = qr.reshape(E, 40, heads, 3 * d).permute(0, 2, 1, 3)
+        q, k, v = t.chunk(3, dim=-1)
+        att = F.softmax(q @ k.transpose(-2, -1) / math.sqrt(d), dim=-1)
+        val = (att @ v).permute(0, 2, 1, 3).reshape(E * 40, heads * d)
+        tape = eng.Tape(True)
+        qv = eng.Var(qkv)
+        vv, att_k = eng.mha_core(tape, qv, E, 40, heads, d)
+        assert rel(vv.t, val) < 1e-5
+        assert rel(att_k, att) < 1e-5
+        g = torch.randn_like(val)
+        val.backward(g)
+        vv.g = g
+        tape.backward()
+        assert rel(qv.g, qr.grad) < 1e-4
