@@ -790,7 +790,638 @@ def adu_postprocess(img):
     return out
 
 
-def __getattr__(name):
-    def _missing(*a, **k):
-        raise NotImplementedError("engine.%s is not built yet" % name)
-    return _missing
+# ------------------------------------------------------------------ Discriminator ops
+def maxpool2(tape, xv, n, hh, ww):
+    c = xv.c
+    y = torch.empty((n, hh // 2, ww // 2, c), dtype=xv.t.dtype, device=xv.t.device)
+    idx = torch.empty((n, hh // 2, ww // 2, c), dtype=torch.uint8, device=xv.t.device)
+    K("iea_maxpool2_fwd", ptr(xv.t), dt(xv.t), n, hh, ww, c, ptr(y), ptr(idx), L.stream())
+    yv = Var(y)
+    if tape.record:
+        def bw():
+            if yv.g is None:
+                return
+            dx = torch.empty_like(xv.t)
+            K("iea_maxpool2_bwd", ptr(yv.g), dt(yv.g), ptr(idx), n, hh, ww, c, ptr(dx), L.stream())
+            add_grad(xv, dx)
+        tape.add(bw)
+    return yv
+
+
+def attn_core(tape, th, ph, gv, n, hw, hwk, ck, cv):
+    o = torch.empty((n, hw, cv), dtype=th.t.dtype, device=th.t.device)
+    lse = _f32(n * hw, th.t.device)
+    K("iea_attn_fwd", ptr(th.t), ptr(ph.t), ptr(gv.t), dt(th.t), n, hw, hwk, ck, cv, ptr(o), ptr(lse), L.stream())
+    ov = Var(o)
+    if tape.record:
+        def bw():
+            if ov.g is None:
+                return
+            dth, dph, dg = torch.empty_like(th.t), torch.empty_like(ph.t), torch.empty_like(gv.t)
+            K("iea_attn_bwd", ptr(ov.g), ptr(th.t), ptr(ph.t), ptr(gv.t), ptr(o), ptr(lse), dt(o), n, hw, hwk, ck,
+              cv, ptr(dth), ptr(dph), ptr(dg), ptr(_f32(n * hw, o.device)), L.stream(), launches=2)
+            add_grad(th, dth)
+            add_grad(ph, dph)
+            add_grad(gv, dg)
+        tape.add(bw)
+    return ov
+
+
+def gamma_residual(tape, ov, xv, gamma):
+    y = torch.empty_like(xv.t)
+    K("iea_gamma_residual", ptr(ov.t), ptr(xv.t), dt(xv.t), ptr(gamma), ptr(y), y.numel(), L.stream())
+    yv = Var(y)
+    if tape.record:
+        def bw():
+            if yv.g is None:
+                return
+            do = torch.empty_like(ov.t)
+            dgm = _f32(1, y.device)
+            K("iea_gamma_residual_bwd", ptr(yv.g), ptr(ov.t), dt(y), ptr(gamma), ptr(do), ptr(dgm),
+              ptr(_f32(600, y.device)), y.numel(), L.stream(), launches=2)
+            if gamma.requires_grad:
+                tape.pgrad(gamma, dgm.view(gamma.shape))
+            add_grad(ov, do)
+            if xv.need:
+                add_grad(xv, yv.g if xv.g is not None else yv.g.clone())
+        tape.add(bw)
+    return yv
+
+
+def relu_sumpool(tape, xv, n, hw):
+    c = xv.c
+    out = torch.empty((n, c), dtype=torch.float32, device=xv.t.device)
+    K("iea_relu_sumpool_fwd", ptr(xv.t), dt(xv.t), n, hw, c, ptr(out), L.stream())
+    ov = Var(out)
+    if tape.record:
+        def bw():
+            if ov.g is None or not xv.need:
+                return
+            dx = torch.empty_like(xv.t)
+            K("iea_relu_sumpool_bwd", ptr(xv.t), dt(xv.t), ptr(ov.g), n, hw, c, ptr(dx), dt(dx), L.stream())
+            add_grad(xv, dx)
+        tape.add(bw)
+    return ov
+
+
+def l2norm(tape, xv, eps=1e-12):
+    x = xv.t
+    rows, dim = x.shape
+    y, nrm = torch.empty_like(x), _f32(rows, x.device)
+    K("iea_l2norm_fwd", ptr(x), rows, dim, eps, ptr(y), ptr(nrm), L.stream())
+    yv = Var(y)
+    if tape.record:
+        def bw():
+            if yv.g is None or not xv.need:
+                return
+            dx = torch.empty_like(x)
+            K("iea_l2norm_bwd", ptr(yv.g), ptr(y), ptr(nrm), rows, dim, eps, ptr(dx), L.stream())
+            add_grad(xv, dx)
+        tape.add(bw)
+    return yv
+
+
+class DPlan:
+    def __init__(self, D):
+        from . import sn_layers as SL
+        self.sn = SNGroup()
+        self.h = {}
+        big = act_dtype()
+        add = lambda m, d: self.h.__setitem__(m, self.sn.add(m, d))
+        add(D.input_conv, big)
+        for stage in D.blocks:
+            for m in stage:
+                if isinstance(m, SL.Attention):
+                    for cv in (m.theta, m.phi, m.g, m.o):
+                        add(cv, big)
+                else:
+                    for cv in (m.conv1, m.conv2, m.conv3, m.conv4):
+                        add(cv, big)
+                    if m.learnable_sc:
+                        add(m.conv_sc, big)
+        add(D.linear0, torch.float32)
+        for blk in D.RR_D.layers:
+            for m in (blk.self_attn.qkv_proj, blk.self_attn.o_proj, blk.linear_net[0], blk.linear_net[3]):
+                add(m, torch.float32)
+        add(D.linear1, torch.float32)
+        add(D.embed, torch.float32)
+
+
+def _dblock(tape, blk, x, n, hh, ww, h_):
+    """Bottleneck DBlock as fused convs (model.py:541-557): the pre-activation ReLUs and the
+    AvgPool2d are conv prologues, the concat shortcut is written straight into the channel window
+    [Cin, Cout) of the output by conv_sc and the pooled identity half is conv4's epilogue residual."""
+    down = blk.downsample is not None
+    cin, cout = blk.in_channels, blk.out_channels
+    h1 = conv(tape, x, h_[blk.conv1], n, hh, ww, 1, bias=blk.conv1.bias, in_relu=blk.preactivation)
+    h2 = conv(tape, h1, h_[blk.conv2], n, hh, ww, 3, bias=blk.conv2.bias, in_relu=True)
+    h3 = conv(tape, h2, h_[blk.conv3], n, hh, ww, 3, bias=blk.conv3.bias, in_relu=True)
+    ho, wo = (hh // 2, ww // 2) if down else (hh, ww)
+    mode = L.IN_POOL2 if down else L.IN_DIRECT
+    y = Var(torch.empty((n, ho, wo, cout), dtype=act_dtype(), device=x.t.device))
+    if blk.learnable_sc:
+        scv = Var(y.t, c0=cin, c=cout - cin)
+        conv(tape, x, h_[blk.conv_sc], n, ho, wo, 1, bias=blk.conv_sc.bias, in_mode=mode, out=scv)
+        y.sc_var = scv
+    conv(tape, h3, h_[blk.conv4], n, ho, wo, 1, bias=blk.conv4.bias, in_relu=True, in_mode=mode, res=x,
+         res_mode=mode, res_c=cin, acc_c0=cin if blk.learnable_sc else -1, out=y)
+    return y, ho, wo
+
+
+def _attention(tape, m, x, n, hh, ww, h_):
+    """layers.py:283-300 with the attention map kept on chip (iea_attn_fwd / iea_attn_bwd)."""
+    ck, cv = m.ch // 8, m.ch // 2
+    th = conv(tape, x, h_[m.theta], n, hh, ww, 1)
+    ph = maxpool2(tape, conv(tape, x, h_[m.phi], n, hh, ww, 1), n, hh, ww)
+    gv = maxpool2(tape, conv(tape, x, h_[m.g], n, hh, ww, 1), n, hh, ww)
+    oc = attn_core(tape, th, ph, gv, n, hh * ww, hh * ww // 4, ck, cv)
+    o = conv(tape, oc, h_[m.o], n, hh, ww, 1)
+    return gamma_residual(tape, o, x, m.gamma)
+
+
+def _d_body(D, tape, xv, y, hh, ww):
+    from . import sn_layers as SL
+    plan = _plan(D, DPlan)
+    sn, h_ = plan.sn, plan.h
+    n = xv.t.shape[0]
+    if n % IMGS:
+        raise ValueError("a batch of %d rows is not a whole number of 40-image events" % n)
+    sn.run(D.training, tape.record)
+    h = conv(tape, xv, h_[D.input_conv], n, hh, ww, 3, bias=D.input_conv.bias)
+    for stage in D.blocks:
+        for m in stage:
+            if isinstance(m, SL.Attention):
+                h = _attention(tape, m, h, n, hh, ww, h_)
+            else:
+                h, hh, ww = _dblock(tape, m, h, n, hh, ww, h_)
+    f = relu_sumpool(tape, h, n, hh * ww)                         # torch.sum(relu(h), [2,3])  model.py:912
+    out = linear(tape, f, h_[D.linear0], bias=D.linear0.bias)      # uses the pre-RRM features  model.py:915
+    proxy = l2norm(tape, embedding(tape, y, D.embed.weight, sn_layer=h_[D.embed]))
+    r = rrm(tape, f, D.RR_D.layers, D.RR_D.norm, h_)
+    e = linear(tape, r, h_[D.linear1], bias=D.linear1.bias)
+    e = l2norm(tape, layernorm(tape, e, D.norm))
+    return [proxy, e, out]
+
+
+def discriminator_forward(D, x, y):
+    x = _plain(x)
+    L.require_device(x)
+    n, c, hh, ww = x.shape
+    if c != 1:
+        raise ValueError("the PXD discriminator takes single-channel images (model.py:730)")
+    y = _plain(y, torch.int64)
+    x4 = x.view(n, hh, ww, 1)  # one channel: NCHW == NHWC
+
+    def body(tape, xv):
+        return _d_body(D, tape, xv, y, hh, ww)
+    proxy, embed, out = run_net(body, [x4], list(D.parameters()))
+    return proxy, embed, out.view(n)
+
+
+# ------------------------------------------------------------------ DiffAugment
+class _AugFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, draws):
+        n, _, h, w = x.shape
+        d = L.AugDraws()
+        keep = []
+
+        def col(t, dtype):
+            t = t.reshape(-1).to(dtype).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        if "brightness" in draws:
+            d.brightness = col(draws["brightness"], torch.float32)
+        if "contrast" in draws:
+            d.contrast = col(draws["contrast"], torch.float32)
+        if "tx" in draws:
+            d.tx, d.ty = col(draws["tx"], torch.int64), col(draws["ty"], torch.int64)
+        if "ox" in draws:
+            d.ox, d.oy = col(draws["ox"], torch.int64), col(draws["oy"], torch.int64)
+            d.cut_h, d.cut_w = int(draws["cut_h"]), int(draws["cut_w"])
+        y = torch.empty_like(x)
+        K("iea_diffaug_fwd", ptr(x), C.byref(d), n, h, w, ptr(y), ptr(_f32(n, x.device)), L.stream(), launches=2)
+        ctx.d, ctx.keep, ctx.geo = d, keep, (n, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, h, w = ctx.geo
+        gy = gy.contiguous()
+        dx = torch.empty_like(gy)
+        K("iea_diffaug_bwd", ptr(gy), C.byref(ctx.d), n, h, w, ptr(dx), ptr(_f32(n, gy.device)), L.stream(),
+          launches=2)
+        return dx, None
+
+
+def diffaug_apply(x, draws):
+    """One fused pass over the image for whichever of brightness / contrast / translation / cutout
+    `draws` holds (saturation is the identity for one channel; its draw is only consumed)."""
+    x = _plain(x)
+    L.require_device(x)
+    if x.shape[1] != 1:
+        raise NotImplementedError("DiffAugment is built for the single-channel PXD images")
+    return _AugFn.apply(x, draws)
+
+
+# ------------------------------------------------------------------ losses
+class _LossFn(torch.autograd.Function):
+    """Generic wrapper: fwd(inputs...) -> (loss tensor(s), saved); bwd(saved, grad) -> input grads."""
+
+    @staticmethod
+    def forward(ctx, fwd, bwd, *xs):
+        out, saved = fwd(*xs)
+        ctx.bwd, ctx.saved, ctx.xs = bwd, saved, xs
+        return out
+
+    @staticmethod
+    def backward(ctx, *g):
+        grads = ctx.bwd(ctx.saved, ctx.xs, [t.contiguous() if t is not None else None for t in g], ctx.needs_input_grad[2:])
+        return (None, None) + tuple(grads)
+
+
+def _events(x):
+    n = x.shape[0]
+    if n % IMGS:
+        raise ValueError("loss input of %d rows is not a whole number of 40-image events" % n)
+    return n // IMGS
+
+
+def loss_hinge_dis(dis_fake, dis_real):
+    f, r = _plain(dis_fake).view(-1), _plain(dis_real).view(-1)
+    L.require_device(f)
+    n = f.numel()
+
+    def fwd(f, r):
+        out = _f32(2, f.device)
+        K("iea_loss_hinge_dis", ptr(f), ptr(r), n, ptr(out), L.stream())
+        return (out[0].clone(), out[1].clone()), None
+
+    def bwd(saved, xs, g, need):
+        dout = torch.stack([g[0] if g[0] is not None else torch.zeros_like(xs[0][0]),
+                            g[1] if g[1] is not None else torch.zeros_like(xs[0][0])]).contiguous()
+        df, dr = torch.empty_like(xs[0]), torch.empty_like(xs[1])
+        K("iea_loss_hinge_dis_bwd", ptr(xs[0]), ptr(xs[1]), ptr(dout), n, ptr(df), ptr(dr), L.stream())
+        return df, dr
+    loss_real, loss_fake = _LossFn.apply(fwd, bwd, f, r)
+    return loss_real, loss_fake
+
+
+def _mean_loss(x, scale):
+    x = _plain(x).view(-1)
+    L.require_device(x)
+    n = x.numel()
+
+    def fwd(x):
+        out = _f32(1, x.device)
+        K("iea_loss_mean", ptr(x), n, scale, ptr(out), L.stream())
+        return out[0], None
+
+    def bwd(saved, xs, g, need):
+        dx = torch.empty_like(xs[0])
+        K("iea_loss_mean_bwd", ptr(g[0]), n, scale, ptr(dx), L.stream())
+        return (dx,)
+    return _LossFn.apply(fwd, bwd, x)
+
+
+def loss_hinge_gen(dis_fake):
+    return _mean_loss(dis_fake, -1.0)
+
+
+def loss_l2(a, b):
+    raise NotImplementedError("l2_loss is only reached with Con_reg=True (config.json:99 Con_reg=false)")
+
+
+def loss_contrastive(embed, proxy, temperature, margin):
+    e, p = _plain(embed), _plain(proxy)
+    L.require_device(e)
+    ev, dim = _events(e), e.shape[1]
+
+    def fwd(e, p):
+        out = _f32(1, e.device)
+        saved = _f32(ev * (2 * IMGS * IMGS + 4 * IMGS + 1), e.device)
+        K("iea_loss_contrastive_fwd", ptr(e), ptr(p), ev, IMGS, dim, temperature, margin, ptr(out), ptr(saved),
+          L.stream(), launches=2)
+        return out[0], saved
+
+    def bwd(saved, xs, g, need):
+        de, dp = torch.empty_like(xs[0]), torch.empty_like(xs[1])
+        K("iea_loss_contrastive_bwd", ptr(xs[0]), ptr(xs[1]), ptr(saved), ptr(g[0]), ev, IMGS, dim, temperature,
+          ptr(de), ptr(dp), L.stream())
+        return de, dp
+    return _LossFn.apply(fwd, bwd, e, p)
+
+
+def loss_iea(k_f, k_r):
+    f, r = _plain(k_f), _plain(k_r).detach()
+    L.require_device(f)
+    ev, dim = _events(f), f.shape[1]
+
+    def fwd(f, r):
+        out = _f32(1, f.device)
+        saved = _f32(ev * (IMGS * IMGS + 1), f.device)
+        K("iea_loss_iea_fwd", ptr(f), ptr(r), ev, IMGS, dim, ptr(out), ptr(saved), L.stream(), launches=2)
+        return out[0], saved
+
+    def bwd(saved, xs, g, need):
+        df = torch.empty_like(xs[0])
+        K("iea_loss_iea_bwd", ptr(xs[0]), ptr(saved), ptr(g[0]), ev, IMGS, dim, ptr(df), L.stream())
+        return df, None
+    return _LossFn.apply(fwd, bwd, f, r)
+
+
+def loss_uniformity(x, t):
+    x = _plain(x)
+    L.require_device(x)
+    ev, dim = _events(x), x.shape[1]
+
+    def fwd(x):
+        out = _f32(1, x.device)
+        saved = _f32(ev * (IMGS * IMGS + 2), x.device)
+        K("iea_loss_unif_fwd", ptr(x), ev, IMGS, dim, t, ptr(out), ptr(saved), L.stream(), launches=2)
+        return out[0], saved
+
+    def bwd(saved, xs, g, need):
+        dx = torch.empty_like(xs[0])
+        K("iea_loss_unif_bwd", ptr(xs[0]), ptr(saved), ptr(g[0]), ev, IMGS, dim, t, ptr(dx), L.stream())
+        return (dx,)
+    return _LossFn.apply(fwd, bwd, x)
+
+
+# ------------------------------------------------------------------ module-level API (stand-alone layers)
+def _mod_plan(mod, mods, dtypes):
+    key = "_iea_modplan"
+    p = mod.__dict__.get(key)
+    if p is None or p[0] != act_dtype():
+        grp = SNGroup()
+        hs = {m: grp.add(m, d) for m, d in zip(mods, dtypes)}
+        p = (act_dtype(), grp, hs)
+        mod.__dict__[key] = p
+    return p[1], p[2]
+
+
+def _to_nhwc(tape, x4):
+    """NCHW torch tensor -> NHWC activation Var (with the inverse as its backward)."""
+    n, c, hh, ww = x4.t.shape
+    out = torch.empty((n, hh, ww, c), dtype=act_dtype(), device=x4.t.device)
+    K("iea_nchw_to_nhwc", ptr(x4.t), dt(x4.t), ptr(out), dt(out), n, c, hh * ww, L.stream())
+    ov = Var(out)
+    if tape.record:
+        def bw():
+            if ov.g is None or not x4.need:
+                return
+            dx = torch.empty_like(x4.t)
+            K("iea_nhwc_to_nchw", ptr(ov.g), dt(ov.g), ptr(dx), dt(dx), n, c, hh * ww, L.stream())
+            add_grad(x4, dx)
+        tape.add(bw)
+    return ov
+
+
+def _to_nchw(tape, xv, n, hh, ww, dtype=torch.float32):
+    c = xv.c
+    out = torch.empty((n, c, hh, ww), dtype=dtype, device=xv.t.device)
+    K("iea_nhwc_to_nchw", ptr(xv.t), dt(xv.t), ptr(out), dt(out), n, c, hh * ww, L.stream())
+    ov = Var(out)
+    if tape.record:
+        def bw():
+            if ov.g is None:
+                return
+            g = torch.empty_like(xv.t)
+            K("iea_nchw_to_nhwc", ptr(ov.g), dt(ov.g), ptr(g), dt(g), n, c, hh * ww, L.stream())
+            add_grad(xv, g)
+        tape.add(bw)
+    return ov
+
+
+def module_conv(m, x):
+    x = _plain(x)
+    L.require_device(x)
+    grp, hs = _mod_plan(m, [m], [act_dtype()])
+    n, _, hh, ww = x.shape
+
+    def body(tape, xv):
+        grp.run(m.training, tape.record)
+        y = conv(tape, _to_nhwc(tape, xv), hs[m], n, hh, ww, m.kernel_size[0], bias=m.bias)
+        return [_to_nchw(tape, y, n, hh, ww)]
+    return run_net(body, [x], list(m.parameters()))
+
+
+def module_linear(m, x):
+    x = _plain(x)
+    L.require_device(x)
+    grp, hs = _mod_plan(m, [m], [torch.float32])
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+
+    def body(tape, xv):
+        grp.run(m.training, tape.record)
+        return [linear(tape, xv, hs[m], bias=m.bias)]
+    return run_net(body, [x2], list(m.parameters())).view(*lead, -1)
+
+
+def module_embedding(m, idx):
+    L.require_device(m.weight)
+    grp, hs = _mod_plan(m, [m], [torch.float32])
+    idx = _plain(idx, torch.int64)
+
+    def body(tape):
+        grp.run(m.training, tape.record)
+        return [embedding(tape, idx.view(-1), m.weight, sn_layer=hs[m])]
+    return run_net(body, [], list(m.parameters())).view(*idx.shape, -1)
+
+
+def sn_weight_standalone(m):
+    """SN.W_(): weight / sigma, differentiable w.r.t. weight (layers.py:151-165)."""
+    L.require_device(m.weight)
+    grp, hs = _mod_plan(m, [m], [torch.float32])
+    rows = m.weight.shape[0]
+    idx = torch.arange(rows, device=m.weight.device)
+
+    def body(tape):
+        grp.run(m.training, tape.record)
+        l = hs[m]
+        w2 = m.weight.view(rows, -1)
+        out = torch.empty_like(w2)
+        K("iea_embedding_fwd", ptr(idx), ptr(w2), ptr(l.inv_sigma()), rows, w2.shape[1], ptr(out), L.stream())
+        v = Var(out)
+        if tape.record:
+            saved = l.saved()
+
+            def bw():
+                if v.g is None:
+                    return
+                # v.g is d(W/sigma) in the master layout [rows][cin][taps]; the kernel wants [rows][taps][cin]
+                G = v.g.view(rows, l.cin, l.taps).transpose(1, 2).contiguous()
+                dw = torch.empty_like(m.weight)
+                K("iea_sn_weight_bwd", ptr(G), 1, ptr(m.weight), ptr(saved[1]), ptr(saved[2]), ptr(saved[0]), 1,
+                  ptr(dw), 0.0, rows, l.cin, l.taps, ptr(_f32(520, dw.device)), L.stream(), launches=2)
+                tape.pgrad(m.weight, dw)
+            tape.add(bw)
+        return [v]
+    return run_net(body, [], [m.weight]).view_as(m.weight)
+
+
+def power_iteration_single(W, u, update, eps):
+    """layers.power_iteration for one singular vector, on the grouped kernel."""
+    L.require_device(W)
+
+    class _M:  # minimal layer record
+        pass
+    m = _M()
+    m.weight, m.u0, m.sv0, m.eps = W.detach().contiguous(), u.view(1, -1).contiguous().clone(), _f32(1, W.device), eps
+    grp = SNGroup()
+    l = grp.add(m, torch.float32)
+    grp.run(True, False)
+    if update:
+        u.view(-1).copy_(m.u0.view(-1))
+    return m.sv0[0].clone(), m.u0.clone(), l.v().view(1, -1).clone()
+
+
+def module_bn(m, x):
+    """layers.bn.forward as stats + affine kernels (stand-alone use; inside G it is fused)."""
+    x = _plain(x)
+    L.require_device(x)
+    n, c, hh, ww = x.shape
+
+    def body(tape, xv):
+        xn = _to_nhwc(tape, xv)
+        ss = bn_affine(tape, xn, n, hh, ww, gain=ptr(m.gain), gain_ld=0, gain_add=0.0, bias=ptr(m.bias), bias_ld=0,
+                       stored_mean=m.stored_mean, stored_var=m.stored_var, training=m.training, eps=m.eps,
+                       momentum=m.momentum, gain_param=m.gain, bias_param=m.bias)
+        return [_to_nchw(tape, affine(tape, xn, ss, n, hh * ww, False), n, hh, ww)]
+    return run_net(body, [x], list(m.parameters()))
+
+
+def affine(tape, xv, ss, n, hw, relu):
+    """y = [relu](x*scale + shift): the stand-alone form of the conv prologue."""
+    c = xv.c
+    y = torch.empty_like(xv.t)
+    K("iea_affine_act", ptr(xv.t), dt(xv.t), ptr(ss.scale), ptr(ss.shift), n, hw, c, int(relu), ptr(y), dt(y), L.stream())
+    yv = Var(y)
+    if tape.record:
+        def bw():
+            if yv.g is None:
+                return
+            # reuse the prologue-backward kernel with an identity 1x1 geometry
+            d = _desc(n, 1, hw, c, c, 1, xv.t, xv.off(), xv.ld, 0, relu, ss.scale, ss.shift, xv.t, None, 0, None,
+                      None, 0, 0, -1, y, y.data_ptr(), c, 0, None)
+            xg, beta = _accum_target(xv)
+            dsc, dsh = torch.empty_like(ss.scale), torch.empty_like(ss.shift)
+            K("iea_conv_input_bwd", C.byref(d), ptr(yv.g), dt(yv.g), ptr(xg), dt(xg), xv.ld, beta, ptr(dsc),
+              ptr(dsh), L.stream())
+            ss.dscale, ss.dshift = dsc, dsh
+        tape.add(bw)
+    return yv
+
+
+def module_ccbn(m, x, y):
+    """layers.ccbn.forward stand-alone: the two SNLinears as one grouped GEMM, stats, affine."""
+    x, y = _plain(x), _plain(y)
+    L.require_device(x)
+    n, c, hh, ww = x.shape
+    key = "_iea_modplan"
+    p = m.__dict__.get(key)
+    if p is None:
+        grp = SNGroup()
+        ls = grp.add_shared([m.gain, m.bias], torch.float32)
+        p = (grp, ls)
+        m.__dict__[key] = p
+    grp, ls = p
+
+    def body(tape, xv, yv):
+        grp.run(m.training, tape.record)
+        wp, wd, cs = grp.colscales[0]
+        gbv = conv(tape, yv, None, n, 1, 1, 1, out_dtype=torch.float32, out_shape=(n, 2 * c),
+                   grouped=(wp, wd, cs, 2 * c, ls))
+        gb, dgb = gbv.t, None
+        if tape.record:
+            dgb = torch.zeros_like(gb)
+            gbv.g = dgb
+        xn = _to_nhwc(tape, xv)
+        ss = bn_affine(tape, xn, n, hh, ww, gain=gb.data_ptr(), gain_ld=2 * c, gain_add=1.0,
+                       bias=gb.data_ptr() + 4 * c, bias_ld=2 * c, stored_mean=m.stored_mean,
+                       stored_var=m.stored_var, training=m.training, eps=m.eps,
+                       dgain=dgb.data_ptr() if dgb is not None else None,
+                       dbias=(dgb.data_ptr() + 4 * c) if dgb is not None else None, dgb_ld=2 * c)
+        return [_to_nchw(tape, affine(tape, xn, ss, n, hh * ww, False), n, hh, ww)]
+    return run_net(body, [x, y], list(m.parameters()))
+
+
+def module_gblock(blk, x, y):
+    raise NotImplementedError("GBlock is executed inside Generator.forward (its ccbn linears are part of the "
+                              "net-level grouped GEMM); call the Generator")
+
+
+def module_dblock(blk, x):
+    x = _plain(x)
+    L.require_device(x)
+    mods = [blk.conv1, blk.conv2, blk.conv3, blk.conv4] + ([blk.conv_sc] if blk.learnable_sc else [])
+    grp, hs = _mod_plan(blk, mods, [act_dtype()] * len(mods))
+    n, _, hh, ww = x.shape
+
+    def body(tape, xv):
+        grp.run(blk.training, tape.record)
+        y, ho, wo = _dblock(tape, blk, _to_nhwc(tape, xv), n, hh, ww, hs)
+        return [_to_nchw(tape, y, n, ho, wo)]
+    return run_net(body, [x], list(blk.parameters()))
+
+
+def module_attention(m, x):
+    x = _plain(x)
+    L.require_device(x)
+    mods = [m.theta, m.phi, m.g, m.o]
+    grp, hs = _mod_plan(m, mods, [act_dtype()] * 4)
+    n, _, hh, ww = x.shape
+
+    def body(tape, xv):
+        grp.run(m.training, tape.record)
+        return [_to_nchw(tape, _attention(tape, m, _to_nhwc(tape, xv), n, hh, ww, hs), n, hh, ww)]
+    return run_net(body, [x], list(m.parameters()))
+
+
+def module_rrm(blocks, final_norm, x):
+    x = _plain(x)
+    L.require_device(x)
+    owner = blocks[0]
+    mods = []
+    for b in blocks:
+        mods += [b.self_attn.qkv_proj, b.self_attn.o_proj, b.linear_net[0], b.linear_net[3]]
+    grp, hs = _mod_plan(owner, mods, [torch.float32] * len(mods))
+    b_, s, e = x.shape
+    if s != IMGS:
+        raise NotImplementedError("the RRM kernels attend over the 40 sensors of an event (seq = 40)")
+    params = [p for b in blocks for p in b.parameters()] + (list(final_norm.parameters()) if final_norm is not None else [])
+
+    def body(tape, xv):
+        grp.run(owner.training, tape.record)
+        return [rrm(tape, xv, blocks, final_norm, hs)]
+    return run_net(body, [x.reshape(b_ * s, e)], params).view(b_, s, e)
+
+
+def module_mha(m, x, return_attention=False):
+    x = _plain(x)
+    L.require_device(x)
+    grp, hs = _mod_plan(m, [m.qkv_proj, m.o_proj], [torch.float32] * 2)
+    b_, s, e = x.shape
+    if s != IMGS:
+        raise NotImplementedError("the RRM kernels attend over the 40 sensors of an event (seq = 40)")
+    keep = {}
+
+    def body(tape, xv):
+        grp.run(m.training, tape.record)
+        qkv = linear(tape, xv, hs[m.qkv_proj], bias=m.qkv_proj.bias)
+        val, att = mha_core(tape, qkv, b_, s, m.num_heads, m.head_dim)
+        keep["att"] = att
+        return [linear(tape, val, hs[m.o_proj], bias=m.o_proj.bias)]
+    o = run_net(body, [x.reshape(b_ * s, e)], list(m.parameters())).view(b_, s, e)
+    return (o, keep["att"]) if return_attention else o
+
+
+def module_sdp(q, k, v):
+    """RRM.scaled_dot_product on (B, h, 40, d) tensors (forward values + attention map)."""
+    q, k, v = _plain(q), _plain(k), _plain(v)
+    L.require_device(q)
+    b_, hds, s, d = q.shape
+    qkv = torch.cat([q, k, v], -1).permute(0, 2, 1, 3).reshape(b_ * s, hds * 3 * d).contiguous()
+    val, att = mha_core(Tape(False), Var(qkv, need=False), b_, s, hds, d)
+    return val.t.view(b_, s, hds, d).permute(0, 2, 1, 3), att

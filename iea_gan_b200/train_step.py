@@ -1,0 +1,119 @@
+"""Host-side driver of one G+D training step on the B200 modules.
+
+The reference's own step function (train_fns.py:20-206) runs unchanged on the
+drop-in modules; this file is the repo's self-contained
+equivalent for the shipped configuration (Contra head, split_D, DiffAugment,
+IEA + uniformity losses, toggle_grads, G ortho-reg, EMA) so that tests and
+bench.py need nothing from the reference tree.  Same order of operations, same
+RNG draws per phase (z_.sample_(), randn rdof inside G, 7 DiffAugment draws).
+"""
+import torch
+
+from . import losses
+
+
+def toggle_grad(model, on):
+    for p in model.parameters():
+        p.requires_grad = on
+
+
+class NormalNoise:
+    """z ~ N(0, var) refreshed in place by sample_() (utils.Distribution 'normal', utils/__init__.py:78-86)."""
+
+    def __init__(self, rows, dim, device, var=1.0):
+        self.t = torch.empty(rows, dim, device=device)
+        self.var = var
+        self.sample_()
+
+    def sample_(self):
+        self.t.normal_(0, self.var)  # the reference passes the variance as std, too (utils/__init__.py:86)
+        return self.t
+
+
+def ortho_(model, strength=1e-4, blacklist=()):
+    """Modified orthogonal regularisation added straight to .grad (utils/__init__.py:843-859):
+    grad += strength * 2 (W W^T * (1 - I)) W, evaluated as 2 (W (W^T W) - diag(|w_i|^2) W) so the
+    rows x rows Gram matrix (24576^2 for G.linear at H_base 3) is never formed."""
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() < 2 or any(p is b for b in blacklist) or p.grad is None:
+                continue
+            w = p.view(p.shape[0], -1)
+            if w.shape[0] <= w.shape[1]:
+                gram = w @ w.t()
+                gram.fill_diagonal_(0.0)
+                g = 2 * (gram @ w)
+            else:
+                g = 2 * (w @ (w.t() @ w) - (w * w).sum(1, keepdim=True) * w)
+            p.grad.add_(g.view_as(p), alpha=strength)
+
+
+class EMA:
+    """utils.apply_ema (utils/__init__.py:809-837) on whole state dicts with fused foreach ops."""
+
+    def __init__(self, source, target, decay=0.9999, start_itr=0):
+        self.decay, self.start_itr = decay, start_itr
+        sd, td = source.state_dict(), target.state_dict()
+        self.src = [sd[k] for k in sd]
+        self.dst = [td[k] for k in sd]
+        with torch.no_grad():
+            torch._foreach_copy_(self.dst, self.src)
+
+    def update(self, itr=None):
+        decay = 0.0 if (itr and itr < self.start_itr) else self.decay
+        with torch.no_grad():
+            fl = [(d, s) for d, s in zip(self.dst, self.src) if d.is_floating_point()]
+            torch._foreach_mul_([d for d, _ in fl], decay)
+            torch._foreach_add_([d for d, _ in fl], [s for _, s in fl], alpha=1 - decay)
+
+
+def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
+    """Returns train(x, y) -> dict of the five floats train_fns.train returns.
+    grad_hook(net) is called after each backward (the data-parallel all-reduce point)."""
+    contra = losses.Conditional_Contrastive_loss(None, config["batch_size"], config["pos_collected_numerator"])
+    state = state if state is not None else {"itr": 0}
+
+    def train(x, y):
+        G.optim.zero_grad()
+        D.optim.zero_grad()
+        toggle_grad(D, True)
+        toggle_grad(G, False)
+        t = 1.0
+        # ---- D step (train_fns.py:49-139)
+        z = z_.sample_()
+        pf, ef, d_fake, pr, er, d_real = GD(z, y, x, y, contra=True, train_G=False, split_D=True,
+                                            diff_aug=config["diff_aug"])
+        l_real, l_fake = losses.loss_hinge_dis(d_fake, d_real)
+        d_loss = l_real + l_fake + config["contra_lambda"] * contra(er, pr, None, y, t, 0)
+        unif_d = losses.unif_loss(er)
+        d_loss = d_loss + config["unif_lambda"] * unif_d
+        d_loss.backward()
+        if grad_hook is not None:
+            grad_hook(D)
+        if config.get("D_ortho", 0.0) > 0.0:
+            ortho_(D, config["D_ortho"])
+        if config.get("clip_norm") is not None:
+            torch.nn.utils.clip_grad_norm_(D.parameters(), config["clip_norm"])
+        D.optim.step()
+        # ---- G step (train_fns.py:142-192)
+        toggle_grad(D, False)
+        toggle_grad(G, True)
+        G.optim.zero_grad()
+        z = z_.sample_()
+        pf, ef, d_fake = GD(z, y, contra=True, train_G=True, split_D=True, diff_aug=config["diff_aug"])
+        g_loss = losses.loss_hinge_gen(d_fake) + config["contra_lambda"] * contra(ef, pf, None, y, t, 0)
+        iea_l = losses.IEA_loss(ef, er)
+        g_loss = g_loss + config["IEA_lambda"] * iea_l + config["unif_lambda"] * losses.unif_loss(ef)
+        g_loss.backward()
+        if grad_hook is not None:
+            grad_hook(G)
+        if config.get("G_ortho", 0.0) > 0.0:
+            ortho_(G, config["G_ortho"], blacklist=list(G.shared.parameters()))
+        if config.get("clip_norm") is not None:  # the reference only steps G inside this branch (train_fns.py:190-192)
+            torch.nn.utils.clip_grad_norm_(G.parameters(), config["clip_norm"])
+            G.optim.step()
+        if ema is not None:
+            ema.update(state["itr"])
+        vals = torch.stack([g_loss.detach(), l_real.detach(), l_fake.detach(), unif_d.detach(), iea_l.detach()]).tolist()
+        return dict(zip(("G_loss", "D_loss_real", "D_loss_fake", "unif_loss_d", "iea_loss"), vals))
+    return train

@@ -1,0 +1,181 @@
+"""Discriminator, DiffAugment, losses and the full G+D train step on the B200 against the
+reference-run golden vectors and the CPU oracle."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def nets(cfg, seed=0):
+    import iea_gan_b200 as P
+    torch.manual_seed(seed)
+    G = P.Generator(**cfg)
+    D = P.Discriminator(**cfg)
+    sg = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    return G.cuda(), D.cuda(), sg, sd
+
+
+# fp32 activations: 3e-4 (summation order); bf16 activations: 5e-2 on embeddings / logits
+@pytest.mark.parametrize("adt,tol", [("fp32", 3e-4), ("bf16", 5e-2)])
+def test_discriminator_forward_vs_golden(small_cfg, golden_fwd, adt, tol):
+    os.environ["IEA_ACT_DTYPE"] = adt
+    try:
+        cfg = dict(small_cfg, device="cuda")
+        _, D, _, _ = nets(cfg)
+        D.train()
+        y = torch.arange(40, device="cuda")
+        x = golden_fwd["x_real"].cuda()
+        with torch.no_grad():
+            p, e, o = D(x, y)
+            assert rel(p, golden_fwd["d_proxy"]) < 1e-5
+            assert rel(e, golden_fwd["d_embed"]) < tol
+            assert rel(o, golden_fwd["d_out"]) < tol
+            D.blocks[1][2].gamma.fill_(0.7)
+            p, e, o = D(x, y)
+            assert rel(e, golden_fwd["d_embed_gamma07"]) < tol
+            assert rel(o, golden_fwd["d_out_gamma07"]) < tol
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)
+
+
+def test_diffaugment_vs_golden_and_grad(golden_fwd):
+    from iea_gan_b200.augment import DiffAugment
+    from oracle import iea_oracle as O
+    for key_in, key_out, seed, shape in (("x_real", "diffaug_out", 104, (40, 64, 64)), ("x_ns", "diffaug_ns_out", 106, (8, 32, 96))):
+        x = golden_fwd[key_in]
+        torch.manual_seed(seed)
+        d = O.diffaug_draws(*shape)  # CPU stream, as in the golden run
+        seq = [d["brightness"], d["saturation"], d["contrast"], d["tx"], d["ty"], d["ox"], d["oy"]]
+        it = iter(seq)
+        real_rand, real_randint = torch.rand, torch.randint
+        try:
+            torch.rand = lambda *a, **k: next(it).cuda()
+            torch.randint = lambda *a, **k: next(it).cuda()
+            xg = x.cuda().requires_grad_(True)
+            out = DiffAugment(xg, policy="color,translation,cutout")
+        finally:
+            torch.rand, torch.randint = real_rand, real_randint
+        assert rel(out, golden_fwd[key_out]) < 1e-6
+        g = torch.randn_like(out)
+        out.backward(g)
+        xr = x.clone().requires_grad_(True)
+        O.diffaugment(xr, d).backward(g.cpu())
+        assert rel(xg.grad, xr.grad) < 1e-5
+
+
+def test_losses_vs_golden_and_grad(golden_fwd):
+    from iea_gan_b200 import losses as LS
+    from oracle import iea_oracle as O
+    e, p, o, ef = (golden_fwd[k] for k in ("d_embed", "d_proxy", "d_out", "embed_fake_rand"))
+    crit = LS.Conditional_Contrastive_loss("cuda", 40, False)
+    eg, pg = e.cuda().requires_grad_(True), p.cuda().requires_grad_(True)
+    lc = crit(eg, pg, None, None, 1.0, 0)
+    assert abs(float(lc) - float(golden_fwd["loss_contra"])) < 1e-5
+    lc.backward()
+    er, pr = e.clone().requires_grad_(True), p.clone().requires_grad_(True)
+    O.contrastive(er, pr).backward()
+    assert rel(eg.grad, er.grad) < 1e-4 and rel(pg.grad, pr.grad) < 1e-4
+    eg = e.cuda().requires_grad_(True)
+    lu = LS.unif_loss(eg)
+    assert abs(float(lu) - float(golden_fwd["loss_unif"])) < 1e-5
+    lu.backward()
+    er = e.clone().requires_grad_(True)
+    O.uniformity(er).backward()
+    assert rel(eg.grad, er.grad) < 1e-4
+    fg = ef.cuda().requires_grad_(True)
+    li = LS.IEA_loss(fg, e.cuda())
+    assert abs(float(li) - float(golden_fwd["loss_iea"])) < 1e-6
+    li.backward()
+    fr = ef.clone().requires_grad_(True)
+    O.iea(fr, e).backward()
+    assert rel(fg.grad, fr.grad) < 1e-4
+    og = o.cuda().requires_grad_(True)
+    a, b = LS.loss_hinge_dis(og * 3 - 0.5, og * 2 + 0.3)
+    c = LS.loss_hinge_gen(og)
+    assert torch.allclose(torch.stack([a, b, c]).cpu(), golden_fwd["loss_hinge"], atol=1e-6)
+    (a + 2 * b + 3 * c).backward()
+    orr = o.clone().requires_grad_(True)
+    a2, b2 = O.hinge_dis(orr * 3 - 0.5, orr * 2 + 0.3)
+    (a2 + 2 * b2 + 3 * O.hinge_gen(orr)).backward()
+    assert rel(og.grad, orr.grad) < 1e-5
+    # two events: mean of per-event losses
+    e2 = torch.cat([e, torch.nn.functional.normalize(torch.randn(40, 1024, generator=torch.Generator().manual_seed(5)), dim=1)])
+    assert abs(float(LS.unif_loss(e2.cuda())) - float(O.uniformity(e2))) < 1e-5
+
+
+@pytest.mark.parametrize("adt", ["fp32", "bf16"])
+def test_train_step_vs_unmodified_train_fns(small_cfg, golden_step, adt):
+    """One full D step + G step (incl. Adam on D between them): the five returned floats, every
+    parameter's gradient norm and selected gradients against the golden run of the reference's
+    unmodified train_fns.train.  Tolerances: fp32 activations 1e-3 on losses / 1e-2 relative on
+    gradient norms; bf16 activations 3e-2 / 0.15 (gradients through 50+ bf16 layers)."""
+    import iea_gan_b200 as P
+    from iea_gan_b200.train_step import make_train_step
+    from oracle import iea_oracle as O
+    os.environ["IEA_ACT_DTYPE"] = adt
+    try:
+        cfg = dict(small_cfg, device="cuda")
+        G, D, _, _ = nets(cfg)
+        G.train(); D.train()
+        GD = P.G_D(G, D)
+        # the golden run's CPU random stream, replayed in order
+        torch.manual_seed(202)
+        draws = []
+        for ph in range(2):
+            z = torch.empty(40, cfg["dim_z"]).normal_(0, 1)
+            rd = torch.randn(40, cfg["rdof_dim"])
+            d = O.diffaug_draws(40, 64, 64)
+            draws.append((z, rd, [d["brightness"], d["saturation"], d["contrast"], d["tx"], d["ty"], d["ox"], d["oy"]]))
+        phase = {"i": -1}
+
+        class Z:
+            def sample_(self):
+                phase["i"] += 1
+                phase["it"] = iter(draws[phase["i"]][2])
+                return draws[phase["i"]][0].cuda()
+        real = (torch.randn, torch.rand, torch.randint)
+        try:
+            torch.randn = lambda *a, **k: draws[phase["i"]][1].cuda() if (len(a) == 2 and a[1] == cfg["rdof_dim"]) else real[0](*a, **k)
+            torch.rand = lambda *a, **k: next(phase["it"]).cuda()
+            torch.randint = lambda *a, **k: next(phase["it"]).cuda()
+            train = make_train_step(G, D, GD, Z(), cfg)
+            losses = train(golden_step["x"].cuda(), torch.arange(40, device="cuda"))
+        finally:
+            torch.randn, torch.rand, torch.randint = real
+        ltol, gtol, ftol = (1e-3, 1e-2, 2e-2) if adt == "fp32" else (3e-2, 0.15, 0.2)
+        for k, v in golden_step["losses"].items():
+            assert abs(losses[k] - v) < ltol * max(1.0, abs(v)), (k, losses[k], v)
+        bad = []
+        # conv biases in front of a batch-norm have an exactly-zero gradient; with bf16 storage the
+        # kernel's value is rounding noise (~1e-4), hence the absolute floor
+        atol = 1e-6 if adt == "fp32" else 3e-4
+        for tag, net, norms in (("G", G, golden_step["g_grad_norm"]), ("D", D, golden_step["d_grad_norm"])):
+            for k, p in net.named_parameters():
+                got = float(p.grad.norm())
+                if abs(got - norms[k]) > gtol * max(norms[k], 1e-6) + atol:
+                    bad.append((tag, k, got, norms[k]))
+        assert not bad, bad[:10]
+        for net, grads in ((G, golden_step["g_grads"]), (D, golden_step["d_grads"])):
+            ps = dict(net.named_parameters())
+            for k, v in grads.items():
+                assert rel(ps[k].grad.reshape(-1)[:65536], v) < ftol, k
+        for k, v in golden_step["g_buffers"].items():
+            assert rel(G.state_dict()[k], v) < (1e-4 if adt == "fp32" else 3e-2), k
+        for k, v in golden_step["d_buffers"].items():
+            assert rel(D.state_dict()[k], v) < (1e-4 if adt == "fp32" else 3e-2), k
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)

@@ -22,6 +22,8 @@ def eng():
         pytest.skip("no CUDA device")
     from iea_gan_b200 import engine, _lib
     _lib.lib()
+    torch.backends.cudnn.allow_tf32 = False   # the torch reference must be real fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     return engine
 
 
