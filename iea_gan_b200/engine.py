@@ -118,7 +118,7 @@ def _f32(n, device):
 class SNLayer:
     """One (optionally spectrally-normalised) weight inside an SNGroup."""
     __slots__ = ("mod", "weight", "rows", "cin", "taps", "spectral", "pack_dtype", "wp", "wd", "index",
-                 "colscale", "group", "wd_ld", "shared")
+                 "colscale", "group", "wd_ld", "shared", "wp_tc", "wd_tc")
 
     def inv_sigma(self):
         return self.group.cur[0][self.index:self.index + 1]
@@ -158,7 +158,7 @@ class SNGroup:
         l.index = len(self.layers)
         l.group = self
         l.colscale = None
-        l.wp = l.wd = None
+        l.wp = l.wd = l.wp_tc = l.wd_tc = None
         l.wd_ld = l.rows
         l.shared = False
         self.layers.append(l)
@@ -213,6 +213,20 @@ class SNGroup:
             n = l.rows * l.cin * l.taps
             l.wp = buf[o:o + n].view(l.rows, l.taps, l.cin)
             l.wd = buf[o + al(n):o + al(n) + n].view(l.cin, l.taps, l.rows)
+        # bf16 copies in the tcgen05 kernel's order for the tensor-core-eligible layers
+        tc_ok = lambda c: c in (16, 32) or (c >= 64 and c % 64 == 0)
+        tc_total, tc_offs = 0, []
+        for l in ls:
+            f = (not l.shared) and l.pack_dtype == torch.bfloat16 and l.rows % 16 == 0 and tc_ok(l.cin)
+            b = (not l.shared) and l.pack_dtype == torch.bfloat16 and l.cin % 16 == 0 and tc_ok(l.rows)
+            n = al(l.rows * l.cin * l.taps)
+            tc_offs.append((tc_total if f else None, tc_total + n if b else None))
+            tc_total += 2 * n if (f or b) else 0
+        self.tc_pack = torch.zeros(max(tc_total, 1), dtype=torch.bfloat16, device=device)
+        for l, (fo, bo) in zip(ls, tc_offs):
+            n = l.rows * l.cin * l.taps
+            l.wp_tc = self.tc_pack[fo:fo + n] if fo is not None else None
+            l.wd_tc = self.tc_pack[bo:bo + n] if bo is not None else None
         chunks, metas, scratch, uo, vo = [], [], 0, 0, 0
         self.u_off, self.v_off = [], []
         for i, l in enumerate(ls):
@@ -259,6 +273,8 @@ class SNGroup:
                     a.colscale_out, a.colscale_n = l.colscale.data_ptr(), l.rows
                 a.pack_fprop = l.wp.data_ptr()
                 a.pack_dgrad = l.wd.data_ptr() if need_bwd else None
+                a.pack_tc_fprop = ptr(l.wp_tc)
+                a.pack_tc_dgrad = ptr(l.wd_tc) if need_bwd else None
                 a.rows, a.cin, a.taps, a.pack_dgrad_ld = l.rows, l.cin, l.taps, l.wd_ld
                 a.pack_dtype = L.F32 if l.pack_dtype == torch.float32 else L.BF16
                 a.spectral = l.spectral
@@ -290,12 +306,13 @@ class SNGroup:
 
 # ------------------------------------------------------------------ fused conv op
 def _desc(n, h, w, cin, cout, k, x_t, x_ptr, x_ld, in_mode, in_relu, scale, shift, wp, out_scale,
-          out_scale_stride, bias, res, res_mode, res_c, acc_c0, y_t, y_ptr, y_ld, act, stats, in_bcast=0):
+          out_scale_stride, bias, res, res_mode, res_c, acc_c0, y_t, y_ptr, y_ld, act, stats, in_bcast=0, wtc=None):
     d = L.ConvDesc()
     d.n, d.h, d.w, d.cin, d.cout, d.ksize = n, h, w, cin, cout, k
     d.x, d.x_dtype, d.x_ld, d.in_mode, d.in_relu = x_ptr, dt(x_t), x_ld, in_mode, int(in_relu)
     d.in_scale, d.in_shift, d.in_bcast = ptr(scale), ptr(shift), in_bcast
     d.wpack, d.w_dtype = wp.data_ptr(), dt(wp)
+    d.wpack_tc = ptr(wtc)
     d.out_scale, d.out_scale_stride = ptr(out_scale), out_scale_stride
     d.bias = ptr(bias)
     if res is not None:
@@ -326,9 +343,11 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
     if grouped is not None:
         wp_t, wd_t, colscale, cout, wls = grouped
         osc, oss = colscale, 1
+        wp_tc = wd_tc = None
     else:
         wp_t, wd_t, colscale, cout, wls = layer.wp, layer.wd, None, layer.rows, [layer]
         osc, oss = layer.inv_sigma(), 0
+        wp_tc, wd_tc = layer.wp_tc, layer.wd_tc
     if out is None:
         od = out_dtype or act_dtype()
         yv = Var(torch.empty(out_shape or (n, h, w, cout), dtype=od, device=dev))
@@ -340,7 +359,7 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
     scale = ss.scale if ss is not None else None
     shift = ss.shift if ss is not None else None
     d = _desc(n, h, w, cin, cout, k, xv.t, xv.off(), xv.ld, in_mode, in_relu, scale, shift, wp_t, osc, oss,
-              bias, res, res_mode, res_c, acc_c0, y, yv.off(), yv.ld, act, st)
+              bias, res, res_mode, res_c, acc_c0, y, yv.off(), yv.ld, act, st, wtc=wp_tc)
     K("iea_conv_fprop", C.byref(d), L.stream())
     if stats:
         rpe = IMGS * h * w
@@ -359,7 +378,7 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
                        None, 0, None, None, 0, 0, 0 if accumulate else -1, dst, dst_ptr, cin, 0, None, in_bcast=1)
         else:
             dd = _desc(n, h, w, cout, cin, k, g_t, g_ptr, g_ld, 0, 0, None, None, wd_t, saved[0][0], 0,
-                       None, None, 0, 0, 0 if accumulate else -1, dst, dst_ptr, cin, 0, None)
+                       None, None, 0, 0, 0 if accumulate else -1, dst, dst_ptr, cin, 0, None, wtc=wd_tc)
         K("iea_conv_fprop", C.byref(dd), L.stream())
 
     def bw():

@@ -54,6 +54,10 @@ typedef struct {
   void* pack_dgrad;      /* optional [cin][taps, spatially flipped][pack_dgrad_ld >= rows] in pack_dtype */
   int32_t rows, cin, taps, colscale_n;
   int32_t pack_dgrad_ld; /* row stride of pack_dgrad (lets several layers share one dgrad matrix) */
+  /* optional bf16 copies in the tcgen05 kernel's smem-image order [tap][k block][16-byte chunk][row][8]:
+   * one contiguous slice per (tap, k block) so the weight operand is a plain TMA bulk copy */
+  void* pack_tc_fprop;   /* rows = cout, k blocks over cin */
+  void* pack_tc_dgrad;   /* rows = cin, k blocks over cout, taps spatially flipped */
   int32_t pack_dtype;    /* iea_dtype */
   int32_t spectral;      /* 0: plain layer, only repack */
   float eps;
@@ -86,6 +90,7 @@ typedef struct {
   const float* in_scale; const float* in_shift;   /* [n][cin] ([cin] when in_bcast) or NULL */
   int32_t in_bcast;
   const void* wpack; int32_t w_dtype;  /* [cout][taps][cin] */
+  const void* wpack_tc;                /* same weights in the tcgen05 order (iea_sn_layer.pack_tc_*) or NULL */
   const float* out_scale; int32_t out_scale_stride; /* 0: scalar, 1: per out channel; NULL: 1 */
   const float* bias;                   /* [cout] or NULL */
   const void* res; int32_t res_dtype, res_ld, res_mode, res_c; /* residual for channels < res_c */

@@ -225,3 +225,60 @@ def test_layernorm_mha_l2norm(eng):
         vv.g = g
         tape.backward()
         assert rel(qv.g, qr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,k,mode,relu,aff,resm,hw", [
+    (16, 16, 3, 0, True, True, None, (16, 16)), (16, 32, 1, 0, True, True, 0, (16, 16)),
+    (32, 32, 3, 1, True, True, 1, (16, 16)), (64, 16, 1, 0, True, True, None, (8, 8)),
+    (64, 64, 3, 2, True, False, 2, (8, 8)), (128, 128, 3, 0, True, True, None, (4, 4)),
+    (512, 128, 1, 0, True, True, None, (4, 4)), (128, 512, 1, 0, False, False, 0, (4, 4)),
+    (32, 64, 1, 0, False, False, None, (12, 20)), (256, 32, 1, 0, True, False, None, (8, 8))])
+def test_conv_tcgen05_matches_generic(eng, cin, cout, k, mode, relu, aff, resm, hw):
+    """The tcgen05/TMEM implicit-GEMM path against the CUDA-core path on the same descriptor: same
+    bf16 inputs and weights, fp32 accumulation in both, so they agree to bf16 output rounding
+    (<= 1 ulp of bf16 = 2^-8 relative per element; 6e-3 relative L2 bound) -- forward, statistics
+    and every backward product that runs through the kernel (data gradient)."""
+    os.environ["IEA_ACT_DTYPE"] = "bf16"
+    try:
+        dev = "cuda"
+        torch.manual_seed(5)
+        h, w = hw
+        n = 40
+        hs, ws = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
+        m = make_sn_conv(cin, cout, k, dev)
+        m.train()
+        grp = eng.SNGroup()
+        l = grp.add(m, torch.bfloat16)
+        grp.run(True, True)
+        assert l.wp_tc is not None
+        x = torch.randn(n, hs, ws, cin, device=dev).bfloat16()
+        scale = (torch.rand(n, cin, device=dev) + 0.5) if aff else None
+        shift = (torch.randn(n, cin, device=dev) * 0.3) if aff else None
+        res = None
+        if resm is not None:
+            rh, rw = (h // 2, w // 2) if resm == 1 else ((2 * h, 2 * w) if resm == 2 else (h, w))
+            res = torch.randn(n, rh, rw, cout + 16, device=dev).bfloat16()
+        outs = {}
+        for impl in ("generic", "tcgen05"):
+            os.environ["IEA_CONV_IMPL"] = impl
+            tape = eng.Tape(True)
+            xv = eng.Var(x)
+            ss = eng.ScaleShift(scale, shift) if aff else None
+            rv = eng.Var(res) if res is not None else None
+            yv = eng.conv(tape, xv, l, n, h, w, k, bias=m.bias, in_mode=mode, in_relu=relu, ss=ss, res=rv,
+                          res_mode=resm or 0, res_c=cout if resm is not None else 0, stats=True)
+            torch.manual_seed(6)
+            yv.g = torch.randn(n, h, w, cout, device=dev).bfloat16()
+            m.weight.requires_grad_(False)
+            m.bias.requires_grad_(False)
+            tape.backward()
+            torch.cuda.synchronize()
+            outs[impl] = (yv.t.float(), yv.bn[0].clone() if yv.bn else None, xv.g.float())
+        a, b = outs["generic"], outs["tcgen05"]
+        assert rel(b[0], a[0]) < 6e-3
+        if a[1] is not None:
+            assert rel(b[1], a[1]) < 6e-3
+        assert rel(b[2], a[2]) < 1e-2
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)
+        os.environ.pop("IEA_CONV_IMPL", None)
