@@ -25,7 +25,7 @@ class SnLayer(C.Structure):
     _fields_ = [("w", vp), ("u_in", vp), ("u_out", vp), ("v_out", vp), ("sigma_out", vp),
                 ("inv_sigma_out", vp), ("colscale_out", vp), ("pack_fprop", vp), ("pack_dgrad", vp),
                 ("rows", i32), ("cin", i32), ("taps", i32), ("colscale_n", i32), ("pack_dgrad_ld", i32),
-                ("pack_tc_fprop", vp), ("pack_tc_dgrad", vp),
+                ("pack_tc_fprop", vp), ("pack_tc_dgrad", vp), ("pack_tc_rows", i32), ("pack_tc_cin", i32),
                 ("pack_dtype", i32), ("spectral", i32), ("eps", f32), ("chunk0", i32), ("nchunks", i32),
                 ("scratch_off", i64)]
 
@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("n", i64), ("h", i32), ("w", i32), ("cin", i32), ("cout", i32), ("ksize", i32),
                 ("x", vp), ("x_dtype", i32), ("x_ld", i32), ("in_mode", i32), ("in_relu", i32),
                 ("in_scale", vp), ("in_shift", vp), ("in_bcast", i32),
-                ("wpack", vp), ("w_dtype", i32), ("wpack_tc", vp),
+                ("wpack", vp), ("w_dtype", i32), ("wpack_tc", vp), ("cout_tc", i32),
                 ("out_scale", vp), ("out_scale_stride", i32), ("bias", vp),
                 ("res", vp), ("res_dtype", i32), ("res_ld", i32), ("res_mode", i32), ("res_c", i32),
                 ("acc_c0", i32), ("y", vp), ("y_dtype", i32), ("y_ld", i32), ("act", i32),

@@ -38,44 +38,76 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const void* x, int x_dtyp
   }
 }
 
-// one thread per channel; events handled sequentially so the running statistics see them in order
-__global__ void bn_finalize_kernel(const float* partials, int events, int tiles, double count, int imgs, int c,
-                                   const float* gain, int64_t gain_ld, float gain_add, const float* bias,
-                                   int64_t bias_ld, float* stored_mean, float* stored_var, int training,
-                                   float momentum, float eps, float* mean_out, float* rstd_out, float* scale,
-                                   float* shift) {
-  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cc >= c) return;
-  float rm = stored_mean ? stored_mean[cc] : 0.f, rv = stored_var ? stored_var[cc] : 1.f;
-  for (int e = 0; e < events; ++e) {
-    float mean, rstd;
-    if (training) {
-      double s1 = 0.0, s2 = 0.0;
-      const float* p = partials + ((int64_t)e * tiles * c + cc) * 2;
-      for (int t = 0; t < tiles; ++t, p += (int64_t)c * 2) { s1 += (double)p[0]; s2 += (double)p[1]; }
-      double m = s1 / count;
-      double var = s2 / count - m * m;
-      if (var < 0.0) var = 0.0;
-      mean = (float)m;
-      rstd = (float)(1.0 / sqrt(var + (double)eps));
-      double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-      rm = (1.f - momentum) * rm + momentum * mean;
-      rv = (1.f - momentum) * rv + momentum * (float)unb;
-    } else {
-      mean = rm;
-      rstd = rsqrtf(rv + eps);
-    }
-    if (mean_out) { mean_out[e * c + cc] = mean; rstd_out[e * c + cc] = rstd; }
-    for (int i = 0; i < imgs; ++i) {
-      int64_t n = (int64_t)e * imgs + i;
-      float gn = gain_add + (gain ? gain[n * gain_ld + cc] : 0.f);
-      float bs = bias ? bias[n * bias_ld + cc] : 0.f;
-      float sc = rstd * gn;
-      scale[n * c + cc] = sc;
-      shift[n * c + cc] = bs - mean * sc;
+// stage 1: per (event, channel) reduce the tile partials in double (fixed order -> deterministic).
+// grid (events, ceil(c/8)); 256 threads = 8 channels x 32 tile lanes.  red[e][c] = (mean, biased var)
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* partials, int tiles, double count, int c,
+                                                        float* mean_out, float* var_out) {
+  __shared__ double r1[256], r2[256];
+  const int e = blockIdx.x, cl = threadIdx.x & 7, tl = threadIdx.x >> 3, cc = blockIdx.y * 8 + cl;
+  double s1 = 0.0, s2 = 0.0;
+  if (cc < c) {
+    const float* p = partials + ((int64_t)e * tiles * c + cc) * 2;
+    for (int t = tl; t < tiles; t += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(p + (int64_t)t * c * 2);
+      s1 += (double)v.x; s2 += (double)v.y;
     }
   }
-  if (training && stored_mean) { stored_mean[cc] = rm; stored_var[cc] = rv; }
+  r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+  __syncthreads();
+  if (tl == 0 && cc < c) {
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < 32; ++l) { a += r1[l * 8 + cl]; b += r2[l * 8 + cl]; }
+    const double m = a / count;
+    double var = b / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean_out[e * c + cc] = (float)m;
+    var_out[e * c + cc] = (float)var;
+  }
+}
+
+// stage 2: one thread per (image, channel): scale/shift; the threads of image 0 also fold the events
+// into the running statistics in order (momentum update is sequential in the events).
+__global__ void bn_affine_kernel(int events, double count, int imgs, int c, const float* gain, int64_t gain_ld,
+                                 float gain_add, const float* bias, int64_t bias_ld, float* stored_mean,
+                                 float* stored_var, int training, float momentum, float eps, float* mean_io,
+                                 float* rstd_io, float* scale, float* shift) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)events * imgs * c;
+  if (idx >= total) return;
+  const int cc = idx % c;
+  const int64_t n = idx / c;
+  const int e = (int)(n / imgs);
+  float mean, rstd;
+  if (training) {
+    mean = mean_io[e * c + cc];
+    rstd = (float)(1.0 / sqrt((double)rstd_io[e * c + cc] + (double)eps));  // rstd_io holds the variance here
+  } else {
+    mean = stored_mean[cc];
+    rstd = rsqrtf(stored_var[cc] + eps);
+  }
+  const float gn = gain_add + (gain ? gain[n * gain_ld + cc] : 0.f);
+  const float bs = bias ? bias[n * bias_ld + cc] : 0.f;
+  const float sc = rstd * gn;
+  scale[n * c + cc] = sc;
+  shift[n * c + cc] = bs - mean * sc;
+}
+__global__ void bn_running_kernel(int events, double count, int c, float* stored_mean, float* stored_var,
+                                  int training, float momentum, float eps, float* mean_io, float* rstd_io) {
+  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc >= c) return;
+  if (!training) {
+    for (int e = 0; e < events; ++e) { mean_io[e * c + cc] = stored_mean[cc]; rstd_io[e * c + cc] = rsqrtf(stored_var[cc] + eps); }
+    return;
+  }
+  float rm = stored_mean ? stored_mean[cc] : 0.f, rv = stored_var ? stored_var[cc] : 1.f;
+  for (int e = 0; e < events; ++e) {
+    const double var = (double)rstd_io[e * c + cc];
+    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * mean_io[e * c + cc];
+    rv = (1.f - momentum) * rv + momentum * (float)unb;
+    rstd_io[e * c + cc] = (float)(1.0 / sqrt(var + (double)eps));  // variance -> rstd, saved for backward
+  }
+  if (stored_mean) { stored_mean[cc] = rm; stored_var[cc] = rv; }
 }
 
 __global__ void bn_finalize_bwd_kernel(const float* dscale, const float* dshift, const float* scale,
@@ -155,9 +187,16 @@ extern "C" int iea_bn_finalize(const float* partials, int events, int tiles_per_
                                const float* bias, int64_t bias_ld, float* stored_mean, float* stored_var,
                                int training, float momentum, float eps, float* mean_out, float* rstd_out,
                                float* scale, float* shift, iea_stream_t stream) {
-  bn_finalize_kernel<<<cdiv(c, 64), 64, 0, (cudaStream_t)stream>>>(
-      partials, events, tiles_per_event, (double)count_per_event, imgs_per_event, c, gain, gain_ld, gain_add, bias,
-      bias_ld, stored_mean, stored_var, training, momentum, eps, mean_out, rstd_out, scale, shift);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)events * imgs_per_event;
+  if (training)
+    bn_reduce_kernel<<<dim3(events, cdiv(c, 8)), 256, 0, st>>>(partials, tiles_per_event, (double)count_per_event, c,
+                                                                 mean_out, rstd_out);
+  bn_affine_kernel<<<cdiv(n * c, 256), 256, 0, st>>>(events, (double)count_per_event, imgs_per_event, c, gain, gain_ld,
+                                                      gain_add, bias, bias_ld, stored_mean, stored_var, training,
+                                                      momentum, eps, mean_out, rstd_out, scale, shift);
+  bn_running_kernel<<<cdiv(c, 64), 64, 0, st>>>(events, (double)count_per_event, c, stored_mean, stored_var, training,
+                                                 momentum, eps, mean_out, rstd_out);
   return check_launch("iea_bn_finalize");
 }
 

@@ -7,6 +7,17 @@ using namespace iea;
 int iea_conv_fprop_generic(const iea_conv_desc* d, cudaStream_t s);
 int iea_conv_fprop_tc(const iea_conv_desc* d, cudaStream_t s);
 int iea_conv_tc_ok(const iea_conv_desc* d);
+int iea_conv_tc2_ok(const iea_conv_desc* d);
+int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s);
+
+// tcgen05 variant selection: resident-weights/patch kernel when it applies, else the streaming one.
+// IEA_TC_VARIANT=stream forces the streaming kernel (used by the tests to cover both).
+static int run_tc(const iea_conv_desc* d, cudaStream_t s) {
+  const char* v = getenv("IEA_TC_VARIANT");
+  const bool force_stream = v && v[0] == 's';
+  if ((!force_stream || !iea_conv_tc_ok(d)) && iea_conv_tc2_ok(d)) return iea_conv_fprop_tc2(d, s);
+  return iea_conv_fprop_tc(d, s);
+}
 
 static int validate(const iea_conv_desc* d) {
   IEA_CHECK_ARG(d != nullptr, "iea_conv_fprop: null descriptor");
@@ -19,7 +30,7 @@ static int validate(const iea_conv_desc* d) {
   return 0;
 }
 
-extern "C" int iea_conv_tc_supported(const iea_conv_desc* d) { return iea_conv_tc_ok(d); }
+extern "C" int iea_conv_tc_supported(const iea_conv_desc* d) { return iea_conv_tc_ok(d) || iea_conv_tc2_ok(d); }
 
 extern "C" int iea_conv_fprop(const iea_conv_desc* d, iea_stream_t stream) {
   int rc = validate(d);
@@ -27,9 +38,9 @@ extern "C" int iea_conv_fprop(const iea_conv_desc* d, iea_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (d->impl == IEA_IMPL_GENERIC) return iea_conv_fprop_generic(d, s);
   if (d->impl == IEA_IMPL_TCGEN05) {
-    IEA_CHECK_ARG(iea_conv_tc_ok(d), "iea_conv_fprop: tcgen05 path requested for an unsupported shape "
+    IEA_CHECK_ARG(iea_conv_tc_ok(d) || iea_conv_tc2_ok(d), "iea_conv_fprop: tcgen05 path requested for an unsupported shape "
                   "(cin=%d cout=%d k=%d)", d->cin, d->cout, d->ksize);
-    return iea_conv_fprop_tc(d, s);
+    return run_tc(d, s);
   }
-  return iea_conv_tc_ok(d) ? iea_conv_fprop_tc(d, s) : iea_conv_fprop_generic(d, s);
+  return (iea_conv_tc_ok(d) || iea_conv_tc2_ok(d)) ? run_tc(d, s) : iea_conv_fprop_generic(d, s);
 }

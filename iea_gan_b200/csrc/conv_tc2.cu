@@ -1,0 +1,470 @@
+// conv_tc2.cu -- tcgen05 / TMEM convolution, "resident weights + staged patch" variant.
+//
+// The heavy IEA-GAN layers are thin (16..64 channels) at high resolution and therefore HBM bound.
+// For them this kernel
+//   * TMA-bulk-loads the whole (1/sigma-free) bf16 weight once per persistent CTA and keeps it in smem;
+//   * stages every input pixel ONCE per tile: a 1x1 conv stages its 128 pixels, a 3x3 conv stages the
+//     18x10 halo patch of a 16x8 output tile and addresses the 9 taps as shifted UMMA descriptors on
+//     that single patch (start address + (dh*10+dw)*16 B, SBO = 160 B), so shared-memory write traffic
+//     is 1.4x the input instead of 9x and each tile costs one global-load round trip instead of nine;
+//   * keeps `depth` patches in flight per CTA with cp.async straight into their final UMMA slots
+//     (Little's law: ~44 KB per SM must be in flight to saturate HBM3e) and applies the fused prologue
+//     (BN affine + ReLU, nearest-up2 by address mapping) IN PLACE on the landed chunks;
+//   * runs the same fused epilogue as conv_tc.cu out of double-buffered TMEM accumulators.
+// Index arithmetic is 32-bit with one division set per tile (not per chunk): at 16 channels the kernel
+// has ~1400 issue slots per tile at the HBM rate, so 64-bit div/mod per chunk would dominate.
+// Layers whose weights do not fit (>= 128-channel 3x3, 512-channel 1x1) use the streaming kernel.
+#include "tc_common.cuh"
+using namespace iea;
+
+namespace tc2 {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int THREADS = 288;
+constexpr int PW = 10, PH = 18;  // 3x3 halo patch of a 16x8 tile
+
+struct Params {
+  iea_conv_desc d;
+  const bf16* wtc;
+  int64_t M;
+  int n_tiles, hw, hs, ws, KB, nkb, BN, taps, tiles_w, tiles_h, npix, stages, uniform_n, depth;
+  uint32_t plane, stage_bytes, w_bytes, stage_off, staging_off, staging_ld, stat_off, bar_off, tmem_cols;
+};
+
+// tile -> (image, top-left output pixel) for 3x3 tiles, first flattened row for 1x1 tiles
+struct Origin { int n, h0, w0; int64_t m0; };
+template <bool IS3>
+__device__ __forceinline__ Origin tile_origin(const Params& p, int tile) {
+  Origin o;
+  if (IS3) {
+    const unsigned t = (unsigned)tile / (unsigned)p.tiles_w;
+    o.w0 = (int)((unsigned)tile - t * (unsigned)p.tiles_w) * 8;
+    o.n = (int)(t / (unsigned)p.tiles_h);
+    o.h0 = (int)(t - (unsigned)o.n * (unsigned)p.tiles_h) * 16;
+    o.m0 = 0;
+  } else {
+    o.m0 = (int64_t)tile * BM; o.n = 0; o.h0 = 0; o.w0 = 0;
+  }
+  return o;
+}
+
+__device__ __forceinline__ uint4 transform(const uint4& raw, const float* sc, const float* sh, bool affine, bool relu) {
+  float f[8];
+  unpack8(raw, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = affine ? fmaf(f[j], sc[j], sh[j]) : f[j];
+    f[j] = relu ? fmaxf(v, 0.f) : v;
+  }
+  return pack8(f);
+}
+
+__device__ __forceinline__ void load_ss(const iea_conv_desc& d, int64_t n, int ci, float* sc, float* sh) {
+  const int64_t si = (d.in_bcast ? 0 : n * d.cin) + ci;
+  const float4 a0 = *reinterpret_cast<const float4*>(d.in_scale + si), a1 = *reinterpret_cast<const float4*>(d.in_scale + si + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(d.in_shift + si), b1 = *reinterpret_cast<const float4*>(d.in_shift + si + 4);
+  sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+  sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+}
+
+template <int CPR, bool IS3>
+__global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(const Params p) {
+  constexpr int NPIX = IS3 ? PH * PW : BM;
+  constexpr int NL = (NPIX * CPR + 127) / 128;  // chunks per producer thread per patch
+  extern __shared__ __align__(128) uint8_t smem[];
+  const iea_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + p.bar_off;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * p.stages + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * p.stages + 2 + b); };
+  const uint32_t w_bar = bar0 + 8u * (2 * p.stages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.bar_off + 8 * (2 * p.stages + 5));
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    // ===================== weight TMA + MMA issuer =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, p.w_bytes);
+      for (uint32_t off = 0; off < p.w_bytes; off += 32768) {
+        const uint32_t nb = p.w_bytes - off < 32768 ? p.w_bytes - off : 32768;
+        bulk_g2s(sbase + off, (const uint8_t*)p.wtc + off, nb, w_bar);
+      }
+      mbar_wait(w_bar, 0);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t lbo_b = p.BN * 16;
+      const uint32_t sbo_a = IS3 ? PW * 16 : 128;
+      uint32_t g = 0;
+      for (int tcount = 0; tcount < my_tiles; ++tcount) {
+        const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(ab), aph ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + ab * p.BN;
+        for (int kb = 0; kb < p.nkb; ++kb, ++g) {
+          const uint32_t s = g % p.stages, ph = (g / p.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a0 = sbase + p.stage_off + s * p.stage_bytes;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const uint32_t a_tap = a0 + (IS3 ? ((tap / 3) * PW + (tap % 3)) * 16 : 0);
+            const uint32_t b_tap = sbase + ((uint32_t)(tap * p.nkb + kb) * CPR) * lbo_b;
+#pragma unroll
+            for (int j = 0; j < CPR / 2; ++j) {
+              const uint64_t da = make_desc(a_tap + 2 * j * p.plane, p.plane, sbo_a);
+              const uint64_t db = make_desc(b_tap + 2 * j * lbo_b, lbo_b, 128);
+              tc_mma(tacc, da, db, idesc, (kb > 0 || tap > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(tfull_bar(ab));
+      }
+    }
+  } else if (warp <= 4) {
+    // ===================== patch producers =====================
+    const int pt = tid - 32;
+    const int cc = pt % CPR;
+    const bool affine = d.in_scale != nullptr;
+    const bool relu = d.in_relu != 0;
+    const bool pool = d.in_mode == IEA_IN_POOL2;
+    const bool flat = !IS3 && d.in_mode == IEA_IN_DIRECT;      // 1x1 on a same-resolution input: pixel index == row
+    const bool slow = pool || (affine && !p.uniform_n) || (!IS3 && !flat);  // rare shapes: per-chunk generic path
+    const int D = p.depth;                                       // patches kept in flight by cp.async
+    const int n_items = my_tiles * p.nkb;
+    const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
+    const bf16* xb = (const bf16*)d.x;
+
+    // generic (slow-path) coordinates of patch pixel pp
+    auto coords_slow = [&](const Origin& o, int pp, int64_t& nn, int& ih, int& iw) -> bool {
+      if (IS3) { nn = o.n; ih = o.h0 - 1 + pp / PW; iw = o.w0 - 1 + pp % PW; }
+      else {
+        const int64_t m = o.m0 + pp;
+        if (m >= p.M) return false;
+        iw = (int)(m % d.w); const int64_t t = m / d.w; ih = (int)(t % d.h); nn = t / d.h;
+      }
+      return (unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w;
+    };
+    // asynchronous copy of this thread's raw chunks of item `it` straight into their final smem slots
+    auto issue = [&](int it) {
+      const int tl = it / p.nkb, kb = it - tl * p.nkb;
+      const uint32_t s = (uint32_t)(it % p.stages), ph = (uint32_t)((it / p.stages) & 1);
+      mbar_wait(empty_bar(s), ph ^ 1);
+      if (slow) return;
+      const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + tl * (int)gridDim.x);
+      const uint32_t a0 = sbase + p.stage_off + s * p.stage_bytes + cc * p.plane;
+      const int ci = kb * p.KB + cc * 8;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        const int pp = (i * 128 + pt) / CPR;
+        if (pp >= NPIX) continue;
+        const bf16* src;
+        bool in;
+        if (IS3) {
+          const int pi = pp / PW, ih = o.h0 - 1 + pi, iw = o.w0 - 1 + (pp - pi * PW);
+          in = (unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w;
+          src = xb + (((int64_t)o.n * p.hs + (ih >> sh_)) * p.ws + (iw >> sh_)) * d.x_ld + ci;
+        } else {
+          in = o.m0 + pp < p.M;
+          src = xb + (o.m0 + pp) * d.x_ld + ci;
+        }
+        if (in) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a0 + pp * 16), "l"(src) : "memory");
+        else asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a0 + pp * 16), "r"(0) : "memory");
+      }
+    };
+
+    for (int k = 0; k < D - 1; ++k) {
+      if (k < n_items) issue(k);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    float sc[8], sh[8];
+    int ss_n = -1, ss_ci = -1;
+    for (int it = 0; it < n_items; ++it) {
+      if (it + D - 1 < n_items) issue(it + D - 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      switch (D) {  // wait until item `it` (this thread's part) has landed
+        case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+      }
+      const int tl = it / p.nkb, kb = it - tl * p.nkb;
+      const uint32_t s = (uint32_t)(it % p.stages);
+      uint8_t* a0 = smem + p.stage_off + s * p.stage_bytes + cc * p.plane;
+      const int ci = kb * p.KB + cc * 8;
+      if (slow) {
+        const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + tl * (int)gridDim.x);
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+          const int pp = (i * 128 + pt) / CPR;
+          if (pp >= NPIX) continue;
+          int64_t nn; int ih, iw;
+          const bool in = coords_slow(o, pp, nn, ih, iw);
+          *reinterpret_cast<uint4*>(a0 + pp * 16) = in ? load_chunk(d, p.hs, p.ws, nn, ih, iw, ci) : make_uint4(0, 0, 0, 0);
+        }
+      } else if (affine || relu) {  // in-place fused prologue on the chunks this thread copied
+        const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + tl * (int)gridDim.x);
+        const int nn = IS3 ? o.n : (int)(o.m0 / p.hw);
+        if (affine && (nn != ss_n || ci != ss_ci)) { load_ss(d, nn, ci, sc, sh); ss_n = nn; ss_ci = ci; }
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+          const int pp = (i * 128 + pt) / CPR;
+          if (pp >= NPIX) continue;
+          bool in;
+          if (IS3) {
+            const int pi = pp / PW, ih = o.h0 - 1 + pi, iw = o.w0 - 1 + (pp - pi * PW);
+            in = (unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w;
+          } else {
+            in = o.m0 + pp < p.M;
+          }
+          if (!in) continue;  // padding stays zero
+          uint4* q = reinterpret_cast<uint4*>(a0 + pp * 16);
+          *q = transform(*q, sc, sh, affine, relu);
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(full_bar(s));
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3, et = q * 32 + lane;  // TMEM lane == tile row
+    uint8_t* stg = smem + p.staging_off;
+    float* stat = reinterpret_cast<float*>(smem + p.stat_off);
+    const float osc0 = (d.out_scale && !d.out_scale_stride) ? d.out_scale[0] : 1.f;
+    const bool need_px = IS3 || (d.res && d.res_mode != IEA_IN_DIRECT);  // (n, oh, ow) only where it is used
+    const int cg = p.BN / 8;
+    for (int tcount = 0; tcount < my_tiles; ++tcount) {
+      const int tile = (int)blockIdx.x + tcount * (int)gridDim.x;
+      const Origin o = tile_origin<IS3>(p, tile);
+      const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+      // this thread's output pixel
+      int64_t m; int nn = 0, oh = 0, ow = 0; bool valid = true;
+      if (IS3) {
+        nn = o.n; oh = o.h0 + (et >> 3); ow = o.w0 + (et & 7);
+        m = ((int64_t)nn * d.h + oh) * d.w + ow;
+      } else {
+        m = o.m0 + et;
+        valid = m < p.M;
+        if (valid && need_px) {
+          const unsigned mm = (unsigned)m, t = mm / (unsigned)d.w;
+          ow = (int)(mm - t * (unsigned)d.w); nn = (int)(t / (unsigned)d.h); oh = (int)(t - (unsigned)nn * (unsigned)d.h);
+        }
+      }
+      mbar_wait(tfull_bar(ab), aph);
+      tc_fence_after();
+      for (int cb = 0; cb < p.BN / 16; ++cb) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.BN + cb * 16, v);
+        const int c0 = cb * 16;
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c0 + j < d.cout) {
+              const float s_ = d.out_scale_stride ? d.out_scale[c0 + j] : osc0;
+              v[j] = d.bias ? fmaf(v[j], s_, d.bias[c0 + j]) : v[j] * s_;
+            }
+          }
+          if (d.res && c0 < d.res_c) {
+            const bf16* rp = (const bf16*)d.res;
+            float f[16];
+            if (d.res_mode == IEA_IN_POOL2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = 0.f;
+              for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                  const bf16* sp = rp + (((int64_t)nn * (2 * d.h) + 2 * oh + a) * (2 * d.w) + 2 * ow + b) * d.res_ld + c0;
+                  float t8[16];
+                  unpack8(*reinterpret_cast<const uint4*>(sp), t8);
+                  unpack8(*reinterpret_cast<const uint4*>(sp + 8), t8 + 8);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] += 0.25f * t8[j];
+                }
+            } else {
+              const bf16* sp = d.res_mode == IEA_IN_UP2
+                                   ? rp + (((int64_t)nn * (d.h >> 1) + (oh >> 1)) * (d.w >> 1) + (ow >> 1)) * d.res_ld + c0
+                                   : rp + m * d.res_ld + c0;
+              unpack8(*reinterpret_cast<const uint4*>(sp), f);
+              unpack8(*reinterpret_cast<const uint4*>(sp + 8), f + 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += f[j];
+          }
+          if (d.acc_c0 >= 0 && c0 >= d.acc_c0) {
+            const bf16* yp = (const bf16*)d.y + m * d.y_ld + c0;
+            float f[16];
+            unpack8(*reinterpret_cast<const uint4*>(yp), f);
+            unpack8(*reinterpret_cast<const uint4*>(yp + 8), f + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += f[j];
+          }
+          if (d.act == IEA_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (d.act == IEA_ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (d.cout < 16) {  // padded output channels (32->1 convs): store the real ones straight from registers
+          if (valid)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < d.cout) st_act(d.y, d.y_dtype, m * d.y_ld + j, v[j]);
+          continue;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)et * p.staging_ld + cb * 32);
+        dst[0] = pack8(v);
+        dst[1] = pack8(v + 8);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(ab));  // accumulator drained: the MMA warp may start the next tile
+      if (d.cout < 16) continue;
+      bar_sync_epi();
+      // coalesced 16-byte stores: rows of the tile are contiguous runs of pixels in NHWC
+      bf16* yb = (bf16*)d.y;
+      for (int i = et; i < BM * cg; i += 128) {
+        const int row = i / cg, g8 = i - row * cg;
+        int64_t m2;
+        if (IS3) m2 = ((int64_t)o.n * d.h + o.h0 + (row >> 3)) * d.w + o.w0 + (row & 7);
+        else { m2 = o.m0 + row; if (m2 >= p.M) continue; }
+        *reinterpret_cast<uint4*>(yb + m2 * d.y_ld + g8 * 8) =
+            *reinterpret_cast<const uint4*>(stg + (size_t)row * p.staging_ld + g8 * 16);
+      }
+      if (d.stats) {  // per-tile column (sum, sum^2) of the rounded outputs; fixed order -> deterministic
+        int parts = 1;
+        while (parts * 2 * cg <= 128) parts *= 2;
+        const int rows_per = BM / parts;
+        for (int w0_ = et; w0_ < cg * parts; w0_ += 128) {
+          const int g8 = w0_ % cg, part = w0_ / cg;
+          float s1[8], s2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+          for (int r = part * rows_per; r < (part + 1) * rows_per; ++r) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(stg + (size_t)r * p.staging_ld + g8 * 16), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            stat[(part * p.BN + g8 * 8 + j) * 2] = s1[j];
+            stat[(part * p.BN + g8 * 8 + j) * 2 + 1] = s2[j];
+          }
+        }
+        bar_sync_epi();
+        for (int c = et; c < p.BN * 2; c += 128) {
+          float a = 0.f;
+          for (int part = 0; part < parts; ++part) a += stat[part * p.BN * 2 + c];
+          d.stats[(int64_t)tile * d.cout * 2 + c] = a;
+        }
+      }
+      bar_sync_epi();  // staging / stat scratch are reused by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+}  // namespace tc2
+
+int iea_conv_tc_base_ok(const iea_conv_desc* d, int padded);
+
+int iea_conv_tc2_ok(const iea_conv_desc* d) {
+  if (!iea_conv_tc_base_ok(d, 1)) return 0;
+  if (d->cout > 256) return 0;
+  const int64_t wbytes = (int64_t)(d->cout < 16 ? 16 : d->cout) * d->cin * d->ksize * d->ksize * 2;
+  if (wbytes > 96 * 1024) return 0;
+  if (d->ksize == 3 && (d->h % 16 || d->w % 8 || d->cin > 64)) return 0;
+  if (d->n * (int64_t)d->h * d->w >= (1ll << 31)) return 0;  // 32-bit pixel arithmetic inside the kernel
+  return 1;
+}
+
+int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
+  tc2::Params p;
+  p.d = *d;
+  p.wtc = (const bf16*)d->wpack_tc;
+  p.M = d->n * (int64_t)d->h * d->w;
+  p.hw = d->h * d->w;
+  p.hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : (d->in_mode == IEA_IN_POOL2 ? d->h * 2 : d->h);
+  p.ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : (d->in_mode == IEA_IN_POOL2 ? d->w * 2 : d->w);
+  p.KB = d->cin < 64 ? d->cin : 64;
+  p.nkb = d->cin / p.KB;
+  p.taps = d->ksize * d->ksize;
+  p.BN = d->cout < 16 ? 16 : d->cout;
+  const bool is3 = d->ksize == 3;
+  p.tiles_w = is3 ? d->w / 8 : 1;
+  p.tiles_h = is3 ? d->h / 16 : 1;
+  p.n_tiles = (int)(is3 ? d->n * (int64_t)p.tiles_w * p.tiles_h : (p.M + 127) / 128);
+  p.npix = is3 ? tc2::PH * tc2::PW : 128;
+  p.uniform_n = is3 ? 1 : (((int64_t)d->h * d->w) % 128 == 0 ? 1 : 0);
+  const int cpr = p.KB / 8;
+  p.plane = (p.npix * 16 + 127) / 128 * 128 + (cpr == 8 ? 64 : 0);
+  p.stage_bytes = (cpr * p.plane + 127) / 128 * 128;
+  p.w_bytes = (uint32_t)((int64_t)p.BN * d->cin * p.taps * 2);
+  p.stage_off = (p.w_bytes + 127) / 128 * 128;
+  p.staging_ld = p.BN * 2 + 16;
+  const uint32_t staging_bytes = (128 * p.staging_ld + 127) / 128 * 128;
+  const uint32_t stat_bytes = 8192;
+  const uint32_t fixed = p.stage_off + staging_bytes + stat_bytes + 256;
+  // ring depth: enough patches in flight to cover HBM latency (~44 KB per SM), bounded by shared memory
+  int stages = 8;
+  while (stages > 3 && fixed + stages * p.stage_bytes > 110 * 1024) --stages;  // prefer 2 CTAs / SM
+  if (stages < 5) {
+    stages = 8;
+    while (stages > 3 && fixed + stages * p.stage_bytes > 200 * 1024) --stages;
+  }
+  IEA_CHECK_ARG(fixed + stages * p.stage_bytes <= 220 * 1024, "iea_conv_fprop(tcgen05 resident): tile does not fit "
+                "shared memory (cin=%d cout=%d k=%d)", d->cin, d->cout, d->ksize);
+  p.depth = stages >= 8 ? 6 : (stages >= 6 ? 4 : (stages >= 5 ? 3 : 2));
+  p.stages = stages;
+  p.staging_off = p.stage_off + stages * p.stage_bytes;
+  p.stat_off = p.staging_off + staging_bytes;
+  p.bar_off = p.stat_off + stat_bytes;
+  const uint32_t smem = p.bar_off + 256;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * p.BN)) cols <<= 1;
+  p.tmem_cols = cols;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int occ = (cpr <= 4 && smem <= 110 * 1024 && cols <= 256) ? 2 : 1;
+  const int cap = sms * occ;
+  const int grid = p.n_tiles < cap ? p.n_tiles : cap;
+  auto launch = [&](auto kern) -> int {
+    IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, tc2::THREADS, smem, s>>>(p);
+    return 0;
+  };
+  int rc;
+  if (is3) rc = cpr == 2 ? launch(tc2::conv_tc2_kernel<2, true>) : (cpr == 4 ? launch(tc2::conv_tc2_kernel<4, true>) : launch(tc2::conv_tc2_kernel<8, true>));
+  else rc = cpr == 2 ? launch(tc2::conv_tc2_kernel<2, false>) : (cpr == 4 ? launch(tc2::conv_tc2_kernel<4, false>) : launch(tc2::conv_tc2_kernel<8, false>));
+  if (rc) return rc;
+  return check_launch("iea_conv_fprop(tcgen05 resident)");
+}

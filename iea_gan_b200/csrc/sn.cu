@@ -57,11 +57,11 @@ __global__ void __launch_bounds__(256) sn_phase_c(const iea_sn_layer* L, const i
       if (l.pack_dgrad) st_act(l.pack_dgrad, l.pack_dtype, ((int64_t)ci * taps + (taps - 1 - tp)) * l.pack_dgrad_ld + i, wv);
       if (l.pack_tc_fprop) {  // [tap][kb][chunk][co][8], k blocks of min(64, cin) input channels
         const int KB = cin < 64 ? cin : 64, kb = ci / KB, c = (ci % KB) >> 3, cpr = KB >> 3, nkb = cin / KB;
-        ((bf16*)l.pack_tc_fprop)[((((int64_t)tp * nkb + kb) * cpr + c) * rows + i) * 8 + (ci & 7)] = __float2bfloat16_rn(wv);
+        ((bf16*)l.pack_tc_fprop)[((((int64_t)tp * nkb + kb) * cpr + c) * l.pack_tc_rows + i) * 8 + (ci & 7)] = __float2bfloat16_rn(wv);
       }
       if (l.pack_tc_dgrad) {  // [tap'][kb][chunk][ci][8], k blocks of min(64, rows) output channels
         const int KB = rows < 64 ? rows : 64, kb = i / KB, c = (i % KB) >> 3, cpr = KB >> 3, nkb = rows / KB;
-        ((bf16*)l.pack_tc_dgrad)[((((int64_t)(taps - 1 - tp) * nkb + kb) * cpr + c) * cin + ci) * 8 + (i & 7)] = __float2bfloat16_rn(wv);
+        ((bf16*)l.pack_tc_dgrad)[((((int64_t)(taps - 1 - tp) * nkb + kb) * cpr + c) * l.pack_tc_cin + ci) * 8 + (i & 7)] = __float2bfloat16_rn(wv);
       }
     }
     if (l.spectral) {

@@ -216,17 +216,19 @@ class SNGroup:
         # bf16 copies in the tcgen05 kernel's order for the tensor-core-eligible layers
         tc_ok = lambda c: c in (16, 32) or (c >= 64 and c % 64 == 0)
         tc_total, tc_offs = 0, []
+        pad16 = lambda c: (c + 15) // 16 * 16
         for l in ls:
-            f = (not l.shared) and l.pack_dtype == torch.bfloat16 and l.rows % 16 == 0 and tc_ok(l.cin)
-            b = (not l.shared) and l.pack_dtype == torch.bfloat16 and l.cin % 16 == 0 and tc_ok(l.rows)
-            n = al(l.rows * l.cin * l.taps)
-            tc_offs.append((tc_total if f else None, tc_total + n if b else None))
-            tc_total += 2 * n if (f or b) else 0
+            # output channels may be padded to 16 (the 32->1 output conv of G, the 32->1 dgrad of D's stem)
+            f = (not l.shared) and l.pack_dtype == torch.bfloat16 and tc_ok(l.cin)
+            b = (not l.shared) and l.pack_dtype == torch.bfloat16 and tc_ok(l.rows)
+            nf, nb = al(pad16(l.rows) * l.cin * l.taps), al(l.rows * pad16(l.cin) * l.taps)
+            tc_offs.append((tc_total if f else None, tc_total + nf if b else None))
+            tc_total += (nf + nb) if (f or b) else 0
         self.tc_pack = torch.zeros(max(tc_total, 1), dtype=torch.bfloat16, device=device)
         for l, (fo, bo) in zip(ls, tc_offs):
-            n = l.rows * l.cin * l.taps
-            l.wp_tc = self.tc_pack[fo:fo + n] if fo is not None else None
-            l.wd_tc = self.tc_pack[bo:bo + n] if bo is not None else None
+            nf, nb = pad16(l.rows) * l.cin * l.taps, l.rows * pad16(l.cin) * l.taps
+            l.wp_tc = self.tc_pack[fo:fo + nf] if fo is not None else None
+            l.wd_tc = self.tc_pack[bo:bo + nb] if bo is not None else None
         chunks, metas, scratch, uo, vo = [], [], 0, 0, 0
         self.u_off, self.v_off = [], []
         for i, l in enumerate(ls):
@@ -275,6 +277,7 @@ class SNGroup:
                 a.pack_dgrad = l.wd.data_ptr() if need_bwd else None
                 a.pack_tc_fprop = ptr(l.wp_tc)
                 a.pack_tc_dgrad = ptr(l.wd_tc) if need_bwd else None
+                a.pack_tc_rows, a.pack_tc_cin = (l.rows + 15) // 16 * 16, (l.cin + 15) // 16 * 16
                 a.rows, a.cin, a.taps, a.pack_dgrad_ld = l.rows, l.cin, l.taps, l.wd_ld
                 a.pack_dtype = L.F32 if l.pack_dtype == torch.float32 else L.BF16
                 a.spectral = l.spectral
@@ -313,6 +316,7 @@ def _desc(n, h, w, cin, cout, k, x_t, x_ptr, x_ld, in_mode, in_relu, scale, shif
     d.in_scale, d.in_shift, d.in_bcast = ptr(scale), ptr(shift), in_bcast
     d.wpack, d.w_dtype = wp.data_ptr(), dt(wp)
     d.wpack_tc = ptr(wtc)
+    d.cout_tc = (cout + 15) // 16 * 16
     d.out_scale, d.out_scale_stride = ptr(out_scale), out_scale_stride
     d.bias = ptr(bias)
     if res is not None:

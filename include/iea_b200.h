@@ -58,6 +58,8 @@ typedef struct {
    * one contiguous slice per (tap, k block) so the weight operand is a plain TMA bulk copy */
   void* pack_tc_fprop;   /* rows = cout, k blocks over cin */
   void* pack_tc_dgrad;   /* rows = cin, k blocks over cout, taps spatially flipped */
+  int32_t pack_tc_rows;  /* row count of the pack_tc_fprop layout (cout rounded up to 16; extra rows stay 0) */
+  int32_t pack_tc_cin;   /* row count of the pack_tc_dgrad layout (cin rounded up to 16) */
   int32_t pack_dtype;    /* iea_dtype */
   int32_t spectral;      /* 0: plain layer, only repack */
   float eps;
@@ -91,6 +93,7 @@ typedef struct {
   int32_t in_bcast;
   const void* wpack; int32_t w_dtype;  /* [cout][taps][cin] */
   const void* wpack_tc;                /* same weights in the tcgen05 order (iea_sn_layer.pack_tc_*) or NULL */
+  int32_t cout_tc;                     /* row count of wpack_tc (cout rounded up to 16); 0: = cout */
   const float* out_scale; int32_t out_scale_stride; /* 0: scalar, 1: per out channel; NULL: 1 */
   const float* bias;                   /* [cout] or NULL */
   const void* res; int32_t res_dtype, res_ld, res_mode, res_c; /* residual for channels < res_c */

@@ -232,13 +232,18 @@ def test_layernorm_mha_l2norm(eng):
     (32, 32, 3, 1, True, True, 1, (16, 16)), (64, 16, 1, 0, True, True, None, (8, 8)),
     (64, 64, 3, 2, True, False, 2, (8, 8)), (128, 128, 3, 0, True, True, None, (4, 4)),
     (512, 128, 1, 0, True, True, None, (4, 4)), (128, 512, 1, 0, False, False, 0, (4, 4)),
-    (32, 64, 1, 0, False, False, None, (12, 20)), (256, 32, 1, 0, True, False, None, (8, 8))])
-def test_conv_tcgen05_matches_generic(eng, cin, cout, k, mode, relu, aff, resm, hw):
+    (32, 64, 1, 0, False, False, None, (12, 20)), (256, 32, 1, 0, True, False, None, (8, 8)),
+    (16, 16, 3, 1, True, True, None, (32, 24)), (64, 64, 3, 0, True, True, 0, (16, 8)),
+    (32, 32, 3, 0, False, False, None, (48, 16)), (64, 256, 1, 2, True, False, 2, (8, 16)),
+    (128, 32, 1, 0, True, True, None, (16, 16)), (16, 64, 1, 0, True, True, 1, (16, 16))])
+@pytest.mark.parametrize("variant", ["resident", "stream"])
+def test_conv_tcgen05_matches_generic(eng, variant, cin, cout, k, mode, relu, aff, resm, hw):
     """The tcgen05/TMEM implicit-GEMM path against the CUDA-core path on the same descriptor: same
     bf16 inputs and weights, fp32 accumulation in both, so they agree to bf16 output rounding
     (<= 1 ulp of bf16 = 2^-8 relative per element; 6e-3 relative L2 bound) -- forward, statistics
     and every backward product that runs through the kernel (data gradient)."""
     os.environ["IEA_ACT_DTYPE"] = "bf16"
+    os.environ["IEA_TC_VARIANT"] = variant
     try:
         dev = "cuda"
         torch.manual_seed(5)
@@ -273,7 +278,9 @@ def test_conv_tcgen05_matches_generic(eng, cin, cout, k, mode, relu, aff, resm, 
             m.bias.requires_grad_(False)
             tape.backward()
             torch.cuda.synchronize()
-            outs[impl] = (yv.t.float(), yv.bn[0].clone() if yv.bn else None, xv.g.float())
+            # statistics: compare per-event totals (the two kernels tile the image differently)
+            st = yv.bn[0].reshape(n // 40, yv.bn[1], cout, 2).sum(1) if yv.bn else None
+            outs[impl] = (yv.t.float(), st, xv.g.float())
         a, b = outs["generic"], outs["tcgen05"]
         assert rel(b[0], a[0]) < 6e-3
         if a[1] is not None:
@@ -282,3 +289,4 @@ def test_conv_tcgen05_matches_generic(eng, cin, cout, k, mode, relu, aff, resm, 
     finally:
         os.environ.pop("IEA_ACT_DTYPE", None)
         os.environ.pop("IEA_CONV_IMPL", None)
+        os.environ.pop("IEA_TC_VARIANT", None)
