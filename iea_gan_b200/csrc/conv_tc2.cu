@@ -24,7 +24,25 @@ constexpr int BM = 128;
 constexpr int THREADS = 288;
 constexpr int PW = 10, PH = 18;  // 3x3 halo patch of a 16x8 tile
 
+// n / d for 0 <= n < 2^31 via one multiply-high (d fixed per launch)
+struct FastDiv { uint32_t mul, shr, d; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d;
+  if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  f.shr = s;
+  f.mul = (uint32_t)(((1ull << (32 + s)) + d - 1) / d - (1ull << 32));  // round-up magic (Granlund-Montgomery)
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  const uint32_t t = __umulhi(n, f.mul);
+  return (t + ((n - t) >> 1)) >> (f.shr - 1);
+}
+
 struct Params {
+  FastDiv fd_tw, fd_th, fd_w, fd_h, fd_hw;
   iea_conv_desc d;
   const bf16* wtc;
   int64_t M;
@@ -38,9 +56,9 @@ template <bool IS3>
 __device__ __forceinline__ Origin tile_origin(const Params& p, int tile) {
   Origin o;
   if (IS3) {
-    const unsigned t = (unsigned)tile / (unsigned)p.tiles_w;
+    const unsigned t = fdiv((unsigned)tile, p.fd_tw);
     o.w0 = (int)((unsigned)tile - t * (unsigned)p.tiles_w) * 8;
-    o.n = (int)(t / (unsigned)p.tiles_h);
+    o.n = (int)fdiv(t, p.fd_th);
     o.h0 = (int)(t - (unsigned)o.n * (unsigned)p.tiles_h) * 16;
     o.m0 = 0;
   } else {
@@ -223,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
         }
       } else if (affine || relu) {  // in-place fused prologue on the chunks this thread copied
         const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + tl * (int)gridDim.x);
-        const int nn = IS3 ? o.n : (int)(o.m0 / p.hw);
+        const int nn = IS3 ? o.n : (int)fdiv((unsigned)o.m0, p.fd_hw);
         if (affine && (nn != ss_n || ci != ss_ci)) { load_ss(d, nn, ci, sc, sh); ss_n = nn; ss_ci = ci; }
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
@@ -250,9 +268,25 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
     const int q = warp & 3, et = q * 32 + lane;  // TMEM lane == tile row
     uint8_t* stg = smem + p.staging_off;
     float* stat = reinterpret_cast<float*>(smem + p.stat_off);
-    const float osc0 = (d.out_scale && !d.out_scale_stride) ? d.out_scale[0] : 1.f;
+    // per-channel epilogue constants (1/sigma or the grouped-GEMM column scale, bias) staged once per CTA
+    float* ep_sc = reinterpret_cast<float*>(smem + p.bar_off + 256);
+    float* ep_bs = ep_sc + p.BN;
+    for (int c = et; c < p.BN; c += 128) {
+      float s_ = 1.f, b_ = 0.f;
+      if (c < d.cout) {
+        if (d.out_scale) s_ = d.out_scale[d.out_scale_stride ? c : 0];
+        if (d.bias) b_ = d.bias[c];
+      }
+      ep_sc[c] = s_; ep_bs[c] = b_;
+    }
+    bar_sync_epi();
     const bool need_px = IS3 || (d.res && d.res_mode != IEA_IN_DIRECT);  // (n, oh, ow) only where it is used
     const int cg = p.BN / 8;
+    const bool cg_pow2 = (cg & (cg - 1)) == 0;
+    const int cg_sh = 31 - __clz(cg);
+    int parts = 1;
+    while (parts * 2 * cg <= 128) parts *= 2;
+    const int rows_per = BM / parts;
     for (int tcount = 0; tcount < my_tiles; ++tcount) {
       const int tile = (int)blockIdx.x + tcount * (int)gridDim.x;
       const Origin o = tile_origin<IS3>(p, tile);
@@ -266,8 +300,8 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
         m = o.m0 + et;
         valid = m < p.M;
         if (valid && need_px) {
-          const unsigned mm = (unsigned)m, t = mm / (unsigned)d.w;
-          ow = (int)(mm - t * (unsigned)d.w); nn = (int)(t / (unsigned)d.h); oh = (int)(t - (unsigned)nn * (unsigned)d.h);
+          const unsigned mm = (unsigned)m, t = fdiv(mm, p.fd_w);
+          ow = (int)(mm - t * (unsigned)d.w); nn = (int)fdiv(t, p.fd_h); oh = (int)(t - (unsigned)nn * (unsigned)d.h);
         }
       }
       mbar_wait(tfull_bar(ab), aph);
@@ -278,11 +312,11 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
         const int c0 = cb * 16;
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (c0 + j < d.cout) {
-              const float s_ = d.out_scale_stride ? d.out_scale[c0 + j] : osc0;
-              v[j] = d.bias ? fmaf(v[j], s_, d.bias[c0 + j]) : v[j] * s_;
-            }
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
+            const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
+            v[4 * j4] = fmaf(v[4 * j4], s4.x, b4.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], s4.y, b4.y);
+            v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], s4.z, b4.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], s4.w, b4.w);
           }
           if (d.res && c0 < d.res_c) {
             const bf16* rp = (const bf16*)d.res;
@@ -346,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
       // coalesced 16-byte stores: rows of the tile are contiguous runs of pixels in NHWC
       bf16* yb = (bf16*)d.y;
       for (int i = et; i < BM * cg; i += 128) {
-        const int row = i / cg, g8 = i - row * cg;
+        const int row = cg_pow2 ? (i >> cg_sh) : i / cg, g8 = i - row * cg;
         int64_t m2;
         if (IS3) m2 = ((int64_t)o.n * d.h + o.h0 + (row >> 3)) * d.w + o.w0 + (row & 7);
         else { m2 = o.m0 + row; if (m2 >= p.M) continue; }
@@ -354,11 +388,8 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
             *reinterpret_cast<const uint4*>(stg + (size_t)row * p.staging_ld + g8 * 16);
       }
       if (d.stats) {  // per-tile column (sum, sum^2) of the rounded outputs; fixed order -> deterministic
-        int parts = 1;
-        while (parts * 2 * cg <= 128) parts *= 2;
-        const int rows_per = BM / parts;
         for (int w0_ = et; w0_ < cg * parts; w0_ += 128) {
-          const int g8 = w0_ % cg, part = w0_ / cg;
+          const int part = cg_pow2 ? (w0_ >> cg_sh) : w0_ / cg, g8 = w0_ - part * cg;
           float s1[8], s2[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -412,6 +443,7 @@ int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
   p.wtc = (const bf16*)d->wpack_tc;
   p.M = d->n * (int64_t)d->h * d->w;
   p.hw = d->h * d->w;
+  p.fd_w = tc2::make_fastdiv(d->w); p.fd_h = tc2::make_fastdiv(d->h); p.fd_hw = tc2::make_fastdiv(p.hw);
   p.hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : (d->in_mode == IEA_IN_POOL2 ? d->h * 2 : d->h);
   p.ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : (d->in_mode == IEA_IN_POOL2 ? d->w * 2 : d->w);
   p.KB = d->cin < 64 ? d->cin : 64;
@@ -422,6 +454,7 @@ int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
   p.tiles_w = is3 ? d->w / 8 : 1;
   p.tiles_h = is3 ? d->h / 16 : 1;
   p.n_tiles = (int)(is3 ? d->n * (int64_t)p.tiles_w * p.tiles_h : (p.M + 127) / 128);
+  p.fd_tw = tc2::make_fastdiv(p.tiles_w); p.fd_th = tc2::make_fastdiv(p.tiles_h);
   p.npix = is3 ? tc2::PH * tc2::PW : 128;
   p.uniform_n = is3 ? 1 : (((int64_t)d->h * d->w) % 128 == 0 ? 1 : 0);
   const int cpr = p.KB / 8;
@@ -432,7 +465,7 @@ int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
   p.staging_ld = p.BN * 2 + 16;
   const uint32_t staging_bytes = (128 * p.staging_ld + 127) / 128 * 128;
   const uint32_t stat_bytes = 8192;
-  const uint32_t fixed = p.stage_off + staging_bytes + stat_bytes + 256;
+  const uint32_t fixed = p.stage_off + staging_bytes + stat_bytes + 256 + 2 * p.BN * 4;
   // ring depth: enough patches in flight to cover HBM latency (~44 KB per SM), bounded by shared memory
   int stages = 8;
   while (stages > 3 && fixed + stages * p.stage_bytes > 110 * 1024) --stages;  // prefer 2 CTAs / SM
@@ -447,7 +480,7 @@ int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
   p.staging_off = p.stage_off + stages * p.stage_bytes;
   p.stat_off = p.staging_off + staging_bytes;
   p.bar_off = p.stat_off + stat_bytes;
-  const uint32_t smem = p.bar_off + 256;
+  const uint32_t smem = p.bar_off + 256 + 2 * p.BN * 4;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.BN)) cols <<= 1;
   p.tmem_cols = cols;

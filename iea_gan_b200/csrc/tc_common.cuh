@@ -26,6 +26,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
+    if (i > 2) __nanosleep(40);  // back off: spinning warps steal issue slots from the working roles
   }
   __trap();  // a pipeline bug must never hang the GPU
 }
