@@ -373,14 +373,134 @@ extern "C" int iea_conv_wgrad(const iea_conv_desc* d, const void* g, int g_dtype
   return check_launch("iea_conv_wgrad");
 }
 
+// vectorised version for bf16 tensors with cin % 8 == 0: grid (pixel chunks, n), 256 threads =
+// (cin/8 sixteen-byte columns) x (pixel lanes); per-CTA partial (dscale, dshift) then a fixed-order reduce.
+namespace {
+__device__ __forceinline__ void unpack8v(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+__device__ __forceinline__ uint4 pack8v(const float* f) {
+  uint4 r; uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]); o[i] = *reinterpret_cast<uint32_t*>(&t); }
+  return r;
+}
+__global__ void __launch_bounds__(256) conv_input_bwd_vec(const iea_conv_desc d, const Geo g, const bf16* da, bf16* dx,
+                                                          int dx_ld, float beta, float* part, int chunks, int px_per_chunk) {
+  extern __shared__ float red[];  // [lanes][cin][2]
+  const int64_t n = blockIdx.y;
+  const int cgs = d.cin >> 3, lanes = 256 / cgs;
+  const int cgi = threadIdx.x % cgs, pl = threadIdx.x / cgs, c0 = cgi * 8;
+  const int npx = g.hs * g.ws;
+  const int p0 = blockIdx.x * px_per_chunk;
+  int p1 = p0 + px_per_chunk; if (p1 > npx) p1 = npx;
+  float sc[8], sh[8], a_s[8], a_h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; a_s[j] = 0.f; a_h[j] = 0.f; }
+  if (d.in_scale && pl < lanes) {
+    const int64_t si = (d.in_bcast ? 0 : n * d.cin) + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = d.in_scale[si + j]; sh[j] = d.in_shift[si + j]; }
+  }
+  const bf16* xb = (const bf16*)d.x;
+  if (pl < lanes)
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const int xh = p / g.ws, xw = p - xh * g.ws;
+      float xv[8], gs[8];
+      unpack8v(*reinterpret_cast<const uint4*>(xb + (n * npx + p) * d.x_ld + c0), xv);
+      if (d.in_mode == IEA_IN_UP2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gs[j] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            float t[8];
+            unpack8v(*reinterpret_cast<const uint4*>(da + ((n * d.h + 2 * xh + a) * (int64_t)d.w + 2 * xw + b) * d.cin + c0), t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gs[j] += t[j];
+          }
+      } else if (d.in_mode == IEA_IN_POOL2) {
+        unpack8v(*reinterpret_cast<const uint4*>(da + ((n * d.h + (xh >> 1)) * (int64_t)d.w + (xw >> 1)) * d.cin + c0), gs);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gs[j] *= 0.25f;
+      } else {
+        unpack8v(*reinterpret_cast<const uint4*>(da + (n * npx + p) * d.cin + c0), gs);
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = fmaf(xv[j], sc[j], sh[j]);
+        if (d.in_relu && pre <= 0.f) gs[j] = 0.f;
+        a_h[j] += gs[j];
+        a_s[j] = fmaf(gs[j], xv[j], a_s[j]);
+        o[j] = gs[j] * sc[j];
+      }
+      if (dx) {
+        bf16* q = dx + (n * npx + p) * dx_ld + c0;
+        if (beta != 0.f) {
+          float old[8];
+          unpack8v(*reinterpret_cast<const uint4*>(q), old);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(beta, old[j], o[j]);
+        }
+        *reinterpret_cast<uint4*>(q) = pack8v(o);
+      }
+    }
+  if (part) {
+    if (pl < lanes)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { red[(pl * d.cin + c0 + j) * 2] = a_s[j]; red[(pl * d.cin + c0 + j) * 2 + 1] = a_h[j]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d.cin * 2; c += 256) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += red[l * d.cin * 2 + c];
+      part[((n * chunks + blockIdx.x) * d.cin) * 2 + c] = t;
+    }
+  }
+}
+__global__ void input_bwd_reduce(const float* part, int64_t n, int chunks, int cin, float* dscale, float* dshift) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * cin) return;
+  const int64_t nn = i / cin; const int c = i - nn * cin;
+  float a = 0.f, b = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    const float* q = part + ((nn * chunks + k) * cin + c) * 2;
+    a += q[0]; b += q[1];
+  }
+  dscale[i] = a; dshift[i] = b;
+}
+}  // namespace
+
 extern "C" int iea_conv_input_bwd(const iea_conv_desc* d, const void* da, int da_dtype, void* dx, int dx_dtype,
-                                  int dx_ld, float beta, float* dscale, float* dshift, iea_stream_t stream) {
+                                  int dx_ld, float beta, float* dscale, float* dshift, float* scratch,
+                                  iea_stream_t stream) {
   Geo g = make_geo(*d);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = d->x_dtype == IEA_BF16 && da_dtype == IEA_BF16 && (!dx || dx_dtype == IEA_BF16) && d->cin % 8 == 0 &&
+                   d->cin <= 2048 && d->x_ld % 8 == 0 && (!dx || dx_ld % 8 == 0) && scratch != nullptr &&
+                   (reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(da) & 15) == 0 &&
+                   (!dx || (reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+  if (vec) {
+    const int npx = g.hs * g.ws;
+    int chunks = npx / 2048;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    const int ppc = (npx + chunks - 1) / chunks;
+    const int lanes = 256 / (d->cin / 8);
+    const size_t smem = (size_t)lanes * d->cin * 2 * sizeof(float);
+    conv_input_bwd_vec<<<dim3(chunks, (unsigned)d->n), 256, smem, st>>>(*d, g, (const bf16*)da, (bf16*)dx, dx_ld, beta,
+                                                                         dscale ? scratch : nullptr, chunks, ppc);
+    if (dscale)
+      input_bwd_reduce<<<cdiv(d->n * d->cin, 256), 256, 0, st>>>(scratch, d->n, chunks, d->cin, dscale, dshift);
+    return check_launch("iea_conv_input_bwd(vec)");
+  }
   int cb = 1;
   while (cb < d->cin && cb < 32) cb <<= 1;
   dim3 grid((unsigned)d->n, cdiv(d->cin, cb));
-  conv_input_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, g, da, da_dtype, dx, dx_dtype, dx_ld, beta,
-                                                                 dscale, dshift, cb);
+  conv_input_bwd_kernel<<<grid, 256, 0, st>>>(*d, g, da, da_dtype, dx, dx_dtype, dx_ld, beta, dscale, dshift, cb);
   return check_launch("iea_conv_input_bwd");
 }
 

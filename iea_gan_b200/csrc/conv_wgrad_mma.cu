@@ -1,0 +1,342 @@
+// conv_wgrad_mma.cu -- weight gradient of the thin, high-resolution convolutions.
+//
+//   dW[co][tap][ci] = sum over pixels  g[px][co] * T(x)[px + tap][ci]
+//
+// The outputs are tiny (16x144 ... 64x576 values) while the reduction runs over 10^6..10^8 pixels, so
+// the kernel is a persistent split-K: every CTA streams pixel tiles (the same 18x10 halo patch /
+// 128-pixel staging, cp.async ring and in-place fused prologue as the forward kernel), keeps the whole
+// dW in registers across all its tiles and writes one fp32 partial per warp group at the end;
+// iea_sn_weight_bwd reduces the partials in a fixed order (deterministic).
+//
+// Why warp-level mma.sync here and not tcgen05: the UMMA M dimension is >= 64 but Cout (and Cin) of the
+// heavy layers is 16..64, and the 9 taps are non-uniformly strided views of the patch, so they cannot
+// be stacked into one UMMA operand.  Padding M to 128 makes the MMA read 8x the useful shared-memory
+// bytes (331 KB per 128-pixel tile at 16 channels = 2.6k cycles, vs ~350 cycles of HBM time).  The
+// m16n8k16 shape matches the 16-channel blocks exactly, ldmatrix takes per-lane row addresses (so the
+// shifted tap views are free) and each g fragment is reused by all 9 taps: ~40 KB of smem reads/tile.
+#include "tc_common.cuh"
+using namespace iea;
+
+namespace wg {
+using namespace tc;
+
+constexpr int PW = 10, PH = 18;
+
+struct FastDiv { uint32_t mul, shr, d; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d;
+  if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  f.shr = s;
+  f.mul = (uint32_t)(((1ull << (32 + s)) + d - 1) / d - (1ull << 32));
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  const uint32_t t = __umulhi(n, f.mul);
+  return (t + ((n - t) >> 1)) >> (f.shr - 1);
+}
+
+struct Params {
+  FastDiv fd_tw, fd_th, fd_hw;
+  iea_conv_desc d;
+  const void* g; int g_dtype, g_ld;
+  float* gpart;
+  int64_t M;
+  int n_tiles, tiles_w, tiles_h, hs, ws, cpa, cpg, cin_eff, cout_eff, stages, depth, P, WP;
+  uint32_t plane_a, plane_g, stage_bytes, g_off;
+};
+
+struct Origin { int n, h0, w0; int64_t m0; };
+template <bool IS3>
+__device__ __forceinline__ Origin tile_origin(const Params& p, int tile) {
+  Origin o;
+  if (IS3) {
+    const unsigned t = fdiv((unsigned)tile, p.fd_tw);
+    o.w0 = (int)((unsigned)tile - t * (unsigned)p.tiles_w) * 8;
+    o.n = (int)fdiv(t, p.fd_th);
+    o.h0 = (int)(t - (unsigned)o.n * (unsigned)p.tiles_h) * 16;
+    o.m0 = 0;
+  } else {
+    o.m0 = (int64_t)tile * 128; o.n = (int)fdiv((unsigned)o.m0, p.fd_hw); o.h0 = 0; o.w0 = 0;
+  }
+  return o;
+}
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int TAPS, int NPAIR>
+__global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
+  constexpr bool IS3 = TAPS == 9;
+  constexpr int NPIX = IS3 ? PH * PW : 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const iea_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const bool affine = d.in_scale != nullptr, relu = d.in_relu != 0;
+  const bool thin_a = d.cin < 16, thin_g = d.cout < 16;  // 1-channel stem input / 1-channel output conv
+  const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
+  const int D = p.depth;
+  const int total_a = NPIX * p.cpa, total_g = 128 * p.cpg;
+
+  float acc[NPAIR][TAPS][2][4];
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[q][t][j][r] = 0.f;
+
+  // conv-resolution coordinates of patch pixel pp; false = padding / beyond the last row
+  auto pix_a = [&](const Origin& o, int pp, int& ih, int& iw, int64_t& m) -> bool {
+    if (IS3) {
+      const int pi = pp / PW;
+      ih = o.h0 - 1 + pi; iw = o.w0 - 1 + (pp - pi * PW);
+      return (unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w;
+    }
+    m = o.m0 + pp;
+    return m < p.M;
+  };
+  auto issue = [&](int it) {
+    const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + it * (int)gridDim.x);
+    const uint32_t s0 = sbase + (uint32_t)(it % p.stages) * p.stage_bytes;
+    // ---- input patch (raw; transformed in place after it landed)
+    for (int e = tid; e < total_a; e += 256) {
+      const int pp = e / p.cpa, c = e - pp * p.cpa;
+      int ih = 0, iw = 0; int64_t m = 0;
+      const bool in = pix_a(o, pp, ih, iw, m);
+      const uint32_t dst = s0 + c * p.plane_a + pp * 16;
+      if (!in) { asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0) : "memory"); continue; }
+      const int64_t pix = IS3 ? (((int64_t)o.n * p.hs + (ih >> sh_)) * p.ws + (iw >> sh_)) : m;
+      if (thin_a) {  // 1 input channel (fp32 or bf16): zero-extend to a 16-byte chunk
+        const float v = c == 0 ? ld_act(d.x, d.x_dtype, pix * d.x_ld) : 0.f;
+        const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(dst), "r"(lo), "r"(0) : "memory");
+      } else {
+        const bf16* src = (const bf16*)d.x + pix * d.x_ld + c * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+    // ---- output-gradient tile: 128 pixels x cout, pixel r = (r>>3, r&7) inside a 16x8 tile
+    for (int e = tid; e < total_g; e += 256) {
+      const int r = e / p.cpg, c = e - r * p.cpg;
+      int64_t m;
+      bool in = true;
+      if (IS3) m = ((int64_t)o.n * d.h + o.h0 + (r >> 3)) * d.w + o.w0 + (r & 7);
+      else { m = o.m0 + r; in = m < p.M; }
+      const uint32_t dst = s0 + p.g_off + c * p.plane_g + r * 16;
+      if (!in) { asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0) : "memory"); continue; }
+      if (thin_g) {
+        uint32_t w4[4] = {0, 0, 0, 0};
+        if (c == 0)
+          for (int j = 0; j < d.cout; ++j) {
+            const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(ld_act(p.g, p.g_dtype, m * p.g_ld + j)));
+            w4[j >> 1] |= h << ((j & 1) * 16);
+          }
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3]) : "memory");
+      } else {
+        const bf16* src = (const bf16*)p.g + m * p.g_ld + c * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+  };
+
+  for (int k = 0; k < D - 1; ++k) {
+    if (k < my_tiles) issue(k);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // warp -> (output block pairs, k-step group)
+  const int nib = p.cin_eff >> 4;  // 16-wide ci blocks
+  int kg = 0, pair0 = 0;
+  if (p.P <= 8) { pair0 = warp % p.P; kg = warp / p.P; } else { pair0 = warp * NPAIR; }
+  float sc[8], sh[8];
+  int ss_n = -1;
+  const int my_c = tid % p.cpa;  // 256 % cpa == 0: the chunk column of this thread is fixed
+
+  for (int it = 0; it < my_tiles; ++it) {
+    if (it + D - 1 < my_tiles) issue(it + D - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    switch (D) {
+      case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+      case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+      case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+      default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    }
+    const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + it * (int)gridDim.x);
+    const uint32_t s0 = sbase + (uint32_t)(it % p.stages) * p.stage_bytes;
+    uint8_t* sp = smem + (size_t)(it % p.stages) * p.stage_bytes;
+    if (affine || relu) {  // fused prologue, in place, on the chunks this thread copied
+      if (affine && o.n != ss_n) {
+        const int64_t si = (d.in_bcast ? 0 : (int64_t)o.n * d.cin) + my_c * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = d.in_scale[si + j]; sh[j] = d.in_shift[si + j]; }
+        ss_n = o.n;
+      }
+      for (int e = tid; e < total_a; e += 256) {
+        const int pp = e / p.cpa;
+        int ih = 0, iw = 0; int64_t m = 0;
+        if (!pix_a(o, pp, ih, iw, m)) continue;
+        uint4* q = reinterpret_cast<uint4*>(sp + my_c * p.plane_a + pp * 16);
+        float f[8];
+        unpack8(*q, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = affine ? fmaf(f[j], sc[j], sh[j]) : f[j];
+          f[j] = relu ? fmaxf(v, 0.f) : v;
+        }
+        *q = pack8(f);
+      }
+    }
+    __syncthreads();
+    // ---- tensor-core accumulation
+    const int mat = lane >> 3, rr = lane & 7;
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) {
+      const int pair = pair0 + q;
+      const int cb = pair / nib, ib = pair - cb * nib;
+      for (int ks = kg; ks < 8; ks += p.WP) {
+        uint32_t a[4];
+        ldsm_x4_t(s0 + p.g_off + (cb * 2 + (mat & 1)) * p.plane_g + (ks * 16 + (mat >> 1) * 8 + rr) * 16, a[0], a[1], a[2], a[3]);
+        const uint32_t brow = s0 + (ib * 2 + (mat >> 1)) * p.plane_a;
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) {
+          int pp;
+          if (IS3) pp = (2 * ks + (mat & 1) + t / 3) * PW + rr + t % 3;   // (i + 1 + dh) * PW + (j + 1 + dw)
+          else pp = ks * 16 + (mat & 1) * 8 + rr;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(brow + pp * 16, b0, b1, b2, b3);
+          mma16816(acc[q][t][0], a, b0, b1);
+          mma16816(acc[q][t][1], a, b2, b3);
+        }
+      }
+    }
+    __syncthreads();  // the stage is overwritten by the cp.async of the next iteration
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // ---- one partial per (CTA, k-step group): gpart[slice][cout][taps][cin]
+  const int64_t slice = (int64_t)blockIdx.x * p.WP + kg;
+  float* out = p.gpart + slice * d.cout * TAPS * d.cin;
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q) {
+    const int pair = pair0 + q;
+    const int cb = pair / nib, ib = pair - cb * nib;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int co = cb * 16 + (lane >> 2) + (r >= 2 ? 8 : 0);
+          const int ci = ib * 16 + j * 8 + 2 * (lane & 3) + (r & 1);
+          if (co < d.cout && ci < d.cin) out[((int64_t)co * TAPS + t) * d.cin + ci] = acc[q][t][j][r];
+        }
+  }
+}
+
+}  // namespace wg
+
+// number of partial slices iea_conv_wgrad_mma will write (0: shape not handled by this kernel)
+static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Params* p, int* npair_out) {
+  const bool thin_a = d->cin < 16, thin_g = d->cout < 16;
+  if (!thin_a && (d->cin % 16 || d->x_dtype != IEA_BF16 || d->x_ld % 8 || (reinterpret_cast<uintptr_t>(d->x) & 15))) return 0;
+  if (thin_a && (d->cin != 1 || d->in_scale || d->in_relu || d->in_mode != IEA_IN_DIRECT)) return 0;
+  if (!thin_g && (d->cout % 16 || g_dtype != IEA_BF16 || g_ld % 8)) return 0;
+  if (thin_g && d->cout > 8) return 0;
+  if (d->in_mode == IEA_IN_POOL2) return 0;
+  const int cin_eff = thin_a ? 16 : d->cin, cout_eff = thin_g ? 16 : d->cout;
+  const bool is3 = d->ksize == 3;
+  if (is3 && (d->h % 16 || d->w % 8)) return 0;
+  if (!is3 && (((int64_t)d->h * d->w) % 128) && d->in_scale) return 0;  // a tile must not straddle images
+  if (!is3 && d->in_mode != IEA_IN_DIRECT) return 0;
+  const int64_t M = d->n * (int64_t)d->h * d->w;
+  if (M >= (1ll << 31) || M < 128 * 64) return 0;  // small problems stay on the generic kernel
+  const int P = (cout_eff / 16) * (cin_eff / 16);
+  int npair = 1, WP = 1;
+  if (P <= 8) { if (8 % P) return 0; WP = 8 / P; }
+  else { if (P % 8) return 0; npair = P / 8; }
+  const int taps = d->ksize * d->ksize;
+  if (npair * taps * 8 > 160) return 0;  // accumulator registers per thread
+  if (taps == 9 ? (npair > 2) : (npair != 1 && npair != 2 && npair != 4 && npair != 8 && npair != 16)) return 0;
+  if (cin_eff / 8 > 256 || 256 % (cin_eff / 8)) return 0;
+  p->d = *d;
+  p->M = M;
+  p->hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : d->h;
+  p->ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : d->w;
+  p->tiles_w = is3 ? d->w / 8 : 1;
+  p->tiles_h = is3 ? d->h / 16 : 1;
+  p->n_tiles = (int)(is3 ? d->n * (int64_t)p->tiles_w * p->tiles_h : (M + 127) / 128);
+  p->fd_tw = wg::make_fastdiv(p->tiles_w); p->fd_th = wg::make_fastdiv(p->tiles_h);
+  p->fd_hw = wg::make_fastdiv(d->h * d->w);
+  p->cpa = cin_eff / 8; p->cpg = cout_eff / 8; p->cin_eff = cin_eff; p->cout_eff = cout_eff;
+  const int npix = is3 ? wg::PH * wg::PW : 128;
+  p->plane_a = (npix * 16 + 127) / 128 * 128;
+  p->plane_g = 128 * 16;
+  p->g_off = p->cpa * p->plane_a;
+  p->stage_bytes = p->g_off + p->cpg * p->plane_g;
+  int stages = 4;
+  while (stages > 2 && stages * p->stage_bytes > 100 * 1024) --stages;
+  if (stages * p->stage_bytes > 200 * 1024) return 0;
+  p->stages = stages;
+  p->depth = stages >= 4 ? 3 : 2;
+  p->P = P; p->WP = WP;
+  *npair_out = npair;
+  return 1;
+}
+
+extern "C" int iea_conv_wgrad_mma_slices(const iea_conv_desc* d, int g_dtype, int g_ld) {
+  wg::Params p; int npair;
+  if (!wgrad_mma_plan(d, g_dtype, g_ld, &p, &npair)) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int occ = p.stages * p.stage_bytes <= 100 * 1024 ? 2 : 1;
+  const int grid = p.n_tiles < sms * occ ? p.n_tiles : sms * occ;
+  return grid * p.WP;
+}
+
+extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* gpart,
+                                  iea_stream_t stream) {
+  wg::Params p; int npair;
+  IEA_CHECK_ARG(wgrad_mma_plan(d, g_dtype, g_ld, &p, &npair), "iea_conv_wgrad_mma: shape not handled (cin=%d cout=%d k=%d)",
+                d->cin, d->cout, d->ksize);
+  p.g = g; p.g_dtype = g_dtype; p.g_ld = g_ld; p.gpart = gpart;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint32_t smem = p.stages * p.stage_bytes;
+  const int occ = smem <= 100 * 1024 ? 2 : 1;
+  const int grid = p.n_tiles < sms * occ ? p.n_tiles : sms * occ;
+  cudaStream_t s = (cudaStream_t)stream;
+  auto launch = [&](auto kern) -> int {
+    IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, s>>>(p);
+    return 0;
+  };
+  int rc = -2;
+  const bool is3 = d->ksize == 3;
+  if (is3) {
+    if (npair == 1) rc = launch(wg::wgrad_mma_kernel<9, 1>);
+    else if (npair == 2) rc = launch(wg::wgrad_mma_kernel<9, 2>);
+  } else {
+    if (npair == 1) rc = launch(wg::wgrad_mma_kernel<1, 1>);
+    else if (npair == 2) rc = launch(wg::wgrad_mma_kernel<1, 2>);
+    else if (npair == 4) rc = launch(wg::wgrad_mma_kernel<1, 4>);
+    else if (npair == 8) rc = launch(wg::wgrad_mma_kernel<1, 8>);
+    else if (npair == 16) rc = launch(wg::wgrad_mma_kernel<1, 16>);
+  }
+  IEA_CHECK_ARG(rc != -2, "iea_conv_wgrad_mma: no kernel instance for %d block pairs per warp", npair);
+  if (rc) return rc;
+  return check_launch("iea_conv_wgrad_mma");
+}

@@ -409,10 +409,15 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
             yv.sc_var.g = g_t  # the shortcut conv wrote channels >= acc_c0 of y: same gradient tensor
         if any(l.weight.requires_grad for l in wls):
             kdim = cin * k * k
-            nsplit = max(1, min(64, M // 4096))
-            gpart = torch.empty((nsplit, cout, kdim), dtype=torch.float32, device=dev)
             dfw = fwd_desc()
-            K("iea_conv_wgrad", C.byref(dfw), g_ptr, dt(g_t), g_ld, ptr(gpart), nsplit, L.stream())
+            nsplit = call("iea_conv_wgrad_mma_slices", C.byref(dfw), dt(g_t), g_ld) if conv_impl() != L.IMPL_GENERIC else 0
+            if nsplit > 0:  # tensor-core split-K over pixel tiles, one partial per (CTA, k-step group)
+                gpart = torch.empty((nsplit, cout, kdim), dtype=torch.float32, device=dev)
+                K("iea_conv_wgrad_mma", C.byref(dfw), g_ptr, dt(g_t), g_ld, ptr(gpart), L.stream())
+            else:
+                nsplit = max(1, min(64, M // 4096))
+                gpart = torch.empty((nsplit, cout, kdim), dtype=torch.float32, device=dev)
+                K("iea_conv_wgrad", C.byref(dfw), g_ptr, dt(g_t), g_ld, ptr(gpart), nsplit, L.stream())
             r0 = 0
             for l, (isg, u_, v_) in zip(wls, saved):
                 if l.weight.requires_grad:
@@ -439,7 +444,7 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
                 ss.dscale, ss.dshift = dsc, dsh
             dfw = fwd_desc()
             K("iea_conv_input_bwd", C.byref(dfw), ptr(da), dt(da), xg_ptr, dt(xg) if xg is not None else 0, xv.ld,
-              beta, ptr(dsc), ptr(dsh), L.stream())
+              beta, ptr(dsc), ptr(dsh), ptr(_f32(n * 64 * cin * 2, dev)), L.stream(), launches=2)
     tape.add(bw)
     return yv
 
@@ -1331,7 +1336,7 @@ def affine(tape, xv, ss, n, hw, relu):
             xg, beta = _accum_target(xv)
             dsc, dsh = torch.empty_like(ss.scale), torch.empty_like(ss.shift)
             K("iea_conv_input_bwd", C.byref(d), ptr(yv.g), dt(yv.g), ptr(xg), dt(xg), xv.ld, beta, ptr(dsc),
-              ptr(dsh), L.stream())
+              ptr(dsh), ptr(_f32(n * 64 * c * 2, y.device)), L.stream(), launches=2)
             ss.dscale, ss.dshift = dsc, dsh
         tape.add(bw)
     return yv

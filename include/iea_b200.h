@@ -111,11 +111,18 @@ int iea_conv_tc_supported(const iea_conv_desc* d /* host */);
 int iea_conv_wgrad(const iea_conv_desc* d /* host; x/T fields and geometry are used */, const void* g,
                    int g_dtype, int g_ld, float* gpart, int nsplit, iea_stream_t stream);
 
+/* tensor-core (mma.sync m16n8k16) split-K weight gradient for the thin high-resolution layers.
+ * iea_conv_wgrad_mma_slices returns the number of partial slices the kernel will write for this shape
+ * (0: shape not handled -> use iea_conv_wgrad); gpart must hold slices*cout*taps*cin floats. */
+int iea_conv_wgrad_mma_slices(const iea_conv_desc* d /* host */, int g_dtype, int g_ld);
+int iea_conv_wgrad_mma(const iea_conv_desc* d /* host */, const void* g, int g_dtype, int g_ld, float* gpart,
+                       iea_stream_t stream);
+
 /* backward of T: da [n][h][w][cin] (at conv resolution) -> dx at x's resolution and the
  * per-(n,c) reductions dscale = sum da*relu'*x, dshift = sum da*relu'.  beta=1 accumulates dx. */
 int iea_conv_input_bwd(const iea_conv_desc* d /* host */, const void* da, int da_dtype, void* dx,
                        int dx_dtype, int dx_ld, float beta, float* dscale, float* dshift,
-                       iea_stream_t stream);
+                       float* scratch /* >= n*64*cin*2 floats, or NULL (slow path) */, iea_stream_t stream);
 
 /* g = (dy [* (1 - y^2) if act == TANH]) + ds1[e][c] + 2*y*ds2[e][c]   (batch-norm statistics path) */
 int iea_conv_out_bwd(const void* dy, int dy_dtype, int dy_ld, const void* y, int y_dtype, int y_ld,

@@ -274,19 +274,47 @@ def test_conv_tcgen05_matches_generic(eng, variant, cin, cout, k, mode, relu, af
                           res_mode=resm or 0, res_c=cout if resm is not None else 0, stats=True)
             torch.manual_seed(6)
             yv.g = torch.randn(n, h, w, cout, device=dev).bfloat16()
-            m.weight.requires_grad_(False)
             m.bias.requires_grad_(False)
             tape.backward()
             torch.cuda.synchronize()
             # statistics: compare per-event totals (the two kernels tile the image differently)
             st = yv.bn[0].reshape(n // 40, yv.bn[1], cout, 2).sum(1) if yv.bn else None
-            outs[impl] = (yv.t.float(), st, xv.g.float())
+            outs[impl] = (yv.t.float(), st, xv.g.float(), tape.pgrads[id(m.weight)].clone())
         a, b = outs["generic"], outs["tcgen05"]
         assert rel(b[0], a[0]) < 6e-3
         if a[1] is not None:
             assert rel(b[1], a[1]) < 6e-3
         assert rel(b[2], a[2]) < 1e-2
+        assert rel(b[3], a[3]) < 1e-2  # weight gradient: mma.sync split-K kernel vs CUDA-core kernel
     finally:
         os.environ.pop("IEA_ACT_DTYPE", None)
         os.environ.pop("IEA_CONV_IMPL", None)
         os.environ.pop("IEA_TC_VARIANT", None)
+
+
+@pytest.mark.parametrize("cin,cout,k,hw,gdt", [(1, 32, 3, (32, 32), "bf16"), (32, 1, 3, (32, 32), "fp32"),
+                                              (128, 32, 1, (16, 16), "bf16"), (64, 128, 1, (16, 16), "bf16")])
+def test_wgrad_mma_thin_and_wide(eng, cin, cout, k, hw, gdt):
+    """The 1-channel stem / output convs (zero-extended operands) and the many-block 1x1 shapes of the
+    tensor-core weight-gradient kernel against the CUDA-core kernel."""
+    from iea_gan_b200 import _lib as L
+    import ctypes as C
+    dev = "cuda"
+    torch.manual_seed(9)
+    n, (h, w) = 40, hw
+    x = torch.randn(n, h, w, cin, device=dev)
+    x = x if cin == 1 else x.bfloat16()
+    g = torch.randn(n, h, w, cout, device=dev)
+    g = g if gdt == "fp32" else g.bfloat16()
+    wp = torch.zeros(cout, k * k, cin, device=dev)
+    y = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+    d = eng._desc(n, h, w, cin, cout, k, x, x.data_ptr(), cin, 0, False, None, None, wp, None, 0, None, None, 0, 0,
+                  -1, y, y.data_ptr(), cout, 0, None)
+    slices = L.call("iea_conv_wgrad_mma_slices", C.byref(d), L.dt(g), cout)
+    assert slices > 0
+    gp = torch.empty(slices, cout, k * k * cin, device=dev)
+    L.call("iea_conv_wgrad_mma", C.byref(d), g.data_ptr(), L.dt(g), cout, gp.data_ptr(), L.stream())
+    ref = torch.empty(8, cout, k * k * cin, device=dev)
+    L.call("iea_conv_wgrad", C.byref(d), g.data_ptr(), L.dt(g), cout, ref.data_ptr(), 8, L.stream())
+    torch.cuda.synchronize()
+    assert rel(gp.sum(0), ref.sum(0)) < 5e-3
