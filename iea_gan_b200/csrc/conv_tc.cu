@@ -272,6 +272,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
 // direct fp32/bf16 store of the real channels) which only the resident-weights kernel implements
 int iea_conv_tc_base_ok(const iea_conv_desc* d, int padded) {
   if (!d->wpack_tc) return 0;
+  // 1-channel input (the discriminator stem, fp32 or bf16 image): the resident kernel zero-extends it
+  const bool thin_a = padded && d->cin == 1 && !d->in_scale && !d->in_relu && d->in_mode == IEA_IN_DIRECT;
+  if (thin_a) {
+    if (d->cout % 16 || d->y_dtype != IEA_BF16 || d->y_ld % 8 || !tc::aligned16(d->y) || !tc::aligned16(d->wpack_tc)) return 0;
+    if (d->res && (d->res_dtype != IEA_BF16 || d->res_ld % 8 || !tc::aligned16(d->res) || d->res_c % 16)) return 0;
+    if (d->acc_c0 >= 0 && d->acc_c0 % 16) return 0;
+    return 1;
+  }
   if (d->cin % 16) return 0;
   if (padded && d->cout < 16) {
     if (d->cout_tc != 16 || d->res || d->acc_c0 >= 0 || d->stats) return 0;

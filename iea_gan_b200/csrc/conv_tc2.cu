@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
     const bool affine = d.in_scale != nullptr;
     const bool relu = d.in_relu != 0;
     const bool pool = d.in_mode == IEA_IN_POOL2;
+    const bool thin_a = d.cin < 16;                             // 1-channel image (D stem): zero-extended chunks
     const bool flat = !IS3 && d.in_mode == IEA_IN_DIRECT;      // 1x1 on a same-resolution input: pixel index == row
     const bool slow = pool || (affine && !p.uniform_n) || (!IS3 && !flat);  // rare shapes: per-chunk generic path
     const int D = p.depth;                                       // patches kept in flight by cp.async
@@ -194,18 +195,25 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
       for (int i = 0; i < NL; ++i) {
         const int pp = (i * 128 + pt) / CPR;
         if (pp >= NPIX) continue;
-        const bf16* src;
+        int64_t pix;
         bool in;
         if (IS3) {
           const int pi = pp / PW, ih = o.h0 - 1 + pi, iw = o.w0 - 1 + (pp - pi * PW);
           in = (unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w;
-          src = xb + (((int64_t)o.n * p.hs + (ih >> sh_)) * p.ws + (iw >> sh_)) * d.x_ld + ci;
+          pix = ((int64_t)o.n * p.hs + (ih >> sh_)) * p.ws + (iw >> sh_);
         } else {
           in = o.m0 + pp < p.M;
-          src = xb + (o.m0 + pp) * d.x_ld + ci;
+          pix = o.m0 + pp;
         }
-        if (in) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a0 + pp * 16), "l"(src) : "memory");
-        else asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a0 + pp * 16), "r"(0) : "memory");
+        if (in && thin_a) {
+          const float v = cc == 0 ? ld_act(d.x, d.x_dtype, pix * d.x_ld) : 0.f;
+          const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(a0 + pp * 16), "r"(lo), "r"(0) : "memory");
+        } else if (in) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a0 + pp * 16), "l"(xb + pix * d.x_ld + ci) : "memory");
+        } else {
+          asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a0 + pp * 16), "r"(0) : "memory");
+        }
       }
     };
 
@@ -430,7 +438,7 @@ int iea_conv_tc_base_ok(const iea_conv_desc* d, int padded);
 int iea_conv_tc2_ok(const iea_conv_desc* d) {
   if (!iea_conv_tc_base_ok(d, 1)) return 0;
   if (d->cout > 256) return 0;
-  const int64_t wbytes = (int64_t)(d->cout < 16 ? 16 : d->cout) * d->cin * d->ksize * d->ksize * 2;
+  const int64_t wbytes = (int64_t)(d->cout < 16 ? 16 : d->cout) * (d->cin < 16 ? 16 : d->cin) * d->ksize * d->ksize * 2;
   if (wbytes > 96 * 1024) return 0;
   if (d->ksize == 3 && (d->h % 16 || d->w % 8 || d->cin > 64)) return 0;
   if (d->n * (int64_t)d->h * d->w >= (1ll << 31)) return 0;  // 32-bit pixel arithmetic inside the kernel
@@ -446,8 +454,9 @@ int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
   p.fd_w = tc2::make_fastdiv(d->w); p.fd_h = tc2::make_fastdiv(d->h); p.fd_hw = tc2::make_fastdiv(p.hw);
   p.hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : (d->in_mode == IEA_IN_POOL2 ? d->h * 2 : d->h);
   p.ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : (d->in_mode == IEA_IN_POOL2 ? d->w * 2 : d->w);
-  p.KB = d->cin < 64 ? d->cin : 64;
-  p.nkb = d->cin / p.KB;
+  const int cin_eff = d->cin < 16 ? 16 : d->cin;  // 1-channel stem: K padded to one 16-wide MMA step
+  p.KB = cin_eff < 64 ? cin_eff : 64;
+  p.nkb = cin_eff / p.KB;
   p.taps = d->ksize * d->ksize;
   p.BN = d->cout < 16 ? 16 : d->cout;
   const bool is3 = d->ksize == 3;
@@ -460,7 +469,7 @@ int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
   const int cpr = p.KB / 8;
   p.plane = (p.npix * 16 + 127) / 128 * 128 + (cpr == 8 ? 64 : 0);
   p.stage_bytes = (cpr * p.plane + 127) / 128 * 128;
-  p.w_bytes = (uint32_t)((int64_t)p.BN * d->cin * p.taps * 2);
+  p.w_bytes = (uint32_t)((int64_t)p.BN * cin_eff * p.taps * 2);
   p.stage_off = (p.w_bytes + 127) / 128 * 128;
   p.staging_ld = p.BN * 2 + 16;
   const uint32_t staging_bytes = (128 * p.staging_ld + 127) / 128 * 128;

@@ -225,9 +225,34 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
     __syncthreads();  // the stage is overwritten by the cp.async of the next iteration
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  // ---- one partial per (CTA, k-step group): gpart[slice][cout][taps][cin]
-  const int64_t slice = (int64_t)blockIdx.x * p.WP + kg;
-  float* out = p.gpart + slice * d.cout * TAPS * d.cin;
+  // ---- fold the k-step groups of the CTA (fixed order), then one partial per CTA:
+  //      gpart[blockIdx.x][cout][taps][cin]
+  if (p.WP > 1) {  // NPAIR == 1 here; scratch [P][TAPS*8][32] floats re-uses the pipeline smem
+    float* scr = reinterpret_cast<float*>(smem);
+    __syncthreads();
+    for (int kgi = 1; kgi < p.WP; ++kgi) {
+      if (kg == kgi) {
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) scr[(pair0 * TAPS * 8 + t * 8 + j * 4 + r) * 32 + lane] = acc[0][t][j][r];
+      }
+      __syncthreads();
+      if (kg == 0) {
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[0][t][j][r] += scr[(pair0 * TAPS * 8 + t * 8 + j * 4 + r) * 32 + lane];
+      }
+      __syncthreads();
+    }
+  }
+  if (kg != 0) return;
+  float* out = p.gpart + (int64_t)blockIdx.x * d.cout * TAPS * d.cin;
 #pragma unroll
   for (int q = 0; q < NPAIR; ++q) {
     const int pair = pair0 + q;
@@ -242,6 +267,15 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
           const int ci = ib * 16 + j * 8 + 2 * (lane & 3) + (r & 1);
           if (co < d.cout && ci < d.cin) out[((int64_t)co * TAPS + t) * d.cin + ci] = acc[q][t][j][r];
         }
+  }
+}
+
+// sum of the per-CTA partials in a fixed order: out[i] = sum_s gpart[s][i]
+__global__ void wgrad_reduce_kernel(const float* gpart, int nsplit, int64_t total, float* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < nsplit; ++s) a += gpart[(int64_t)s * total + i];
+    out[i] = a;
   }
 }
 
@@ -303,7 +337,7 @@ extern "C" int iea_conv_wgrad_mma_slices(const iea_conv_desc* d, int g_dtype, in
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int occ = p.stages * p.stage_bytes <= 100 * 1024 ? 2 : 1;
   const int grid = p.n_tiles < sms * occ ? p.n_tiles : sms * occ;
-  return grid * p.WP;
+  return grid + 1;  // grid per-CTA partials + one slot for their sum (slice 0 after the call)
 }
 
 extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* gpart,
@@ -315,10 +349,15 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint32_t smem = p.stages * p.stage_bytes;
+  const int taps_ = d->ksize * d->ksize;
+  uint32_t smem = p.stages * p.stage_bytes;
   const int occ = smem <= 100 * 1024 ? 2 : 1;
+  if (p.WP > 1 && smem < (uint32_t)(p.P * taps_ * 8 * 32 * 4)) smem = p.P * taps_ * 8 * 32 * 4;  // fold scratch
   const int grid = p.n_tiles < sms * occ ? p.n_tiles : sms * occ;
   cudaStream_t s = (cudaStream_t)stream;
+  const int64_t total = (int64_t)d->cout * taps_ * d->cin;
+  float* parts = gpart + total;  // slices 1..grid hold the per-CTA partials, slice 0 receives their sum
+  p.gpart = parts;
   auto launch = [&](auto kern) -> int {
     IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 256, smem, s>>>(p);
@@ -338,5 +377,8 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
   }
   IEA_CHECK_ARG(rc != -2, "iea_conv_wgrad_mma: no kernel instance for %d block pairs per warp", npair);
   if (rc) return rc;
+  int rb = (int)((total + 255) / 256);
+  if (rb > 592) rb = 592;
+  wg::wgrad_reduce_kernel<<<rb, 256, 0, s>>>(parts, grid, total, gpart);
   return check_launch("iea_conv_wgrad_mma");
 }

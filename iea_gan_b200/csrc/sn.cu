@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256) sn_phase_c(const iea_sn_layer* L, const i
       if (l.pack_fprop) st_act(l.pack_fprop, l.pack_dtype, ((int64_t)i * taps + tp) * cin + ci, wv);
       if (l.pack_dgrad) st_act(l.pack_dgrad, l.pack_dtype, ((int64_t)ci * taps + (taps - 1 - tp)) * l.pack_dgrad_ld + i, wv);
       if (l.pack_tc_fprop) {  // [tap][kb][chunk][co][8], k blocks of min(64, cin) input channels
-        const int KB = cin < 64 ? cin : 64, kb = ci / KB, c = (ci % KB) >> 3, cpr = KB >> 3, nkb = cin / KB;
+        const int cin_p = l.pack_tc_cin;  // cin rounded up to 16 (1-channel stem)
+        const int KB = cin_p < 64 ? cin_p : 64, kb = ci / KB, c = (ci % KB) >> 3, cpr = KB >> 3, nkb = cin_p / KB;
         ((bf16*)l.pack_tc_fprop)[((((int64_t)tp * nkb + kb) * cpr + c) * l.pack_tc_rows + i) * 8 + (ci & 7)] = __float2bfloat16_rn(wv);
       }
       if (l.pack_tc_dgrad) {  // [tap'][kb][chunk][ci][8], k blocks of min(64, rows) output channels

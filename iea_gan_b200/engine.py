@@ -219,14 +219,14 @@ class SNGroup:
         pad16 = lambda c: (c + 15) // 16 * 16
         for l in ls:
             # output channels may be padded to 16 (the 32->1 output conv of G, the 32->1 dgrad of D's stem)
-            f = (not l.shared) and l.pack_dtype == torch.bfloat16 and tc_ok(l.cin)
+            f = (not l.shared) and l.pack_dtype == torch.bfloat16 and tc_ok(pad16(l.cin))
             b = (not l.shared) and l.pack_dtype == torch.bfloat16 and tc_ok(l.rows)
-            nf, nb = al(pad16(l.rows) * l.cin * l.taps), al(l.rows * pad16(l.cin) * l.taps)
+            nf, nb = al(pad16(l.rows) * pad16(l.cin) * l.taps), al(l.rows * pad16(l.cin) * l.taps)
             tc_offs.append((tc_total if f else None, tc_total + nf if b else None))
             tc_total += (nf + nb) if (f or b) else 0
         self.tc_pack = torch.zeros(max(tc_total, 1), dtype=torch.bfloat16, device=device)
         for l, (fo, bo) in zip(ls, tc_offs):
-            nf, nb = pad16(l.rows) * l.cin * l.taps, l.rows * pad16(l.cin) * l.taps
+            nf, nb = pad16(l.rows) * pad16(l.cin) * l.taps, l.rows * pad16(l.cin) * l.taps
             l.wp_tc = self.tc_pack[fo:fo + nf] if fo is not None else None
             l.wd_tc = self.tc_pack[bo:bo + nb] if bo is not None else None
         chunks, metas, scratch, uo, vo = [], [], 0, 0, 0
@@ -413,7 +413,8 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
             nsplit = call("iea_conv_wgrad_mma_slices", C.byref(dfw), dt(g_t), g_ld) if conv_impl() != L.IMPL_GENERIC else 0
             if nsplit > 0:  # tensor-core split-K over pixel tiles, one partial per (CTA, k-step group)
                 gpart = torch.empty((nsplit, cout, kdim), dtype=torch.float32, device=dev)
-                K("iea_conv_wgrad_mma", C.byref(dfw), g_ptr, dt(g_t), g_ld, ptr(gpart), L.stream())
+                K("iea_conv_wgrad_mma", C.byref(dfw), g_ptr, dt(g_t), g_ld, ptr(gpart), L.stream(), launches=2)
+                gpart, nsplit = gpart[:1], 1  # slice 0 now holds the sum of the per-CTA partials
             else:
                 nsplit = max(1, min(64, M // 4096))
                 gpart = torch.empty((nsplit, cout, kdim), dtype=torch.float32, device=dev)
@@ -432,7 +433,7 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
             xg, beta = _accum_target(xv)
             dgrad_into(g_t, g_ptr, g_ld, xg, xg.data_ptr(), beta != 0.0)
         elif xv.need or ss is not None:
-            da = torch.empty((M, cin), dtype=g_t.dtype, device=dev)
+            da = torch.empty((M, cin), dtype=act_dtype(), device=dev)
             dgrad_into(g_t, g_ptr, g_ld, da, da.data_ptr(), False)
             xg, beta, xg_ptr = None, 0.0, None
             if xv.need:

@@ -113,7 +113,8 @@ int iea_conv_wgrad(const iea_conv_desc* d /* host; x/T fields and geometry are u
 
 /* tensor-core (mma.sync m16n8k16) split-K weight gradient for the thin high-resolution layers.
  * iea_conv_wgrad_mma_slices returns the number of partial slices the kernel will write for this shape
- * (0: shape not handled -> use iea_conv_wgrad); gpart must hold slices*cout*taps*cin floats. */
+ * (0: shape not handled -> use iea_conv_wgrad); gpart must hold slices*cout*taps*cin floats.  On return
+ * slice 0 holds the fixed-order sum of the per-CTA partials (pass it to iea_sn_weight_bwd with nsplit 1). */
 int iea_conv_wgrad_mma_slices(const iea_conv_desc* d /* host */, int g_dtype, int g_ld);
 int iea_conv_wgrad_mma(const iea_conv_desc* d /* host */, const void* g, int g_dtype, int g_ld, float* gpart,
                        iea_stream_t stream);

@@ -317,4 +317,4 @@ def test_wgrad_mma_thin_and_wide(eng, cin, cout, k, hw, gdt):
     ref = torch.empty(8, cout, k * k * cin, device=dev)
     L.call("iea_conv_wgrad", C.byref(d), g.data_ptr(), L.dt(g), cout, ref.data_ptr(), 8, L.stream())
     torch.cuda.synchronize()
-    assert rel(gp.sum(0), ref.sum(0)) < 5e-3
+    assert rel(gp[0], ref.sum(0)) < 5e-3  # slice 0 = fixed-order sum of the per-CTA partials
