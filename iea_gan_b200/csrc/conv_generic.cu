@@ -513,13 +513,96 @@ extern "C" int iea_conv_out_bwd(const void* dy, int dy_dtype, int dy_ld, const v
   return check_launch("iea_conv_out_bwd");
 }
 
+// ---- vectorised (bf16, 8 channels per 16-byte load) versions of the two bandwidth-bound adjoints ----
+namespace {
+__global__ void __launch_bounds__(256) colsum_part_vec(const bf16* g, int g_ld, int64_t rows, int c, float* part,
+                                                       int64_t rows_per_block) {
+  extern __shared__ float red[];  // [lanes][c]
+  const int cgs = c >> 3, lanes = 256 / cgs;
+  const int cgi = threadIdx.x % cgs, pl = threadIdx.x / cgs;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block; if (r1 > rows) r1 = rows;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (pl < lanes)
+    for (int64_t m = r0 + pl; m < r1; m += lanes) {
+      float f[8];
+      unpack8v(*reinterpret_cast<const uint4*>(g + m * g_ld + cgi * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += f[j];
+    }
+  if (pl < lanes)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[pl * c + cgi * 8 + j] = a[j];
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < c; cc += 256) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[l * c + cc];
+    part[(int64_t)blockIdx.x * c + cc] = t;
+  }
+}
+// dres (at the residual's resolution) from g (at the conv resolution); one thread per (pixel, 8 channels)
+__global__ void residual_bwd_vec(const bf16* g, int g_ld, int64_t n, int h, int w, int res_c, int res_mode, bf16* dres,
+                                 int dres_ld, int dres_c, float beta) {
+  const int hs = res_mode == IEA_IN_UP2 ? h / 2 : (res_mode == IEA_IN_POOL2 ? h * 2 : h);
+  const int ws = res_mode == IEA_IN_UP2 ? w / 2 : (res_mode == IEA_IN_POOL2 ? w * 2 : w);
+  const int cgs = dres_c >> 3;
+  const int64_t total = n * hs * (int64_t)ws * cgs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cgi = (int)(i % cgs); const int64_t p = i / cgs;
+    const int c0 = cgi * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (c0 < res_c) {
+      if (res_mode == IEA_IN_DIRECT) {
+        unpack8v(*reinterpret_cast<const uint4*>(g + p * g_ld + c0), v);
+      } else {
+        const int xw = (int)(p % ws); const int64_t t = p / ws; const int xh = (int)(t % hs); const int64_t nn = t / hs;
+        if (res_mode == IEA_IN_UP2) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              float f[8];
+              unpack8v(*reinterpret_cast<const uint4*>(g + ((nn * h + 2 * xh + a) * (int64_t)w + 2 * xw + b) * g_ld + c0), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += f[j];
+            }
+        } else {
+          unpack8v(*reinterpret_cast<const uint4*>(g + ((nn * h + (xh >> 1)) * (int64_t)w + (xw >> 1)) * g_ld + c0), v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= 0.25f;
+        }
+      }
+    }
+    bf16* q = dres + p * dres_ld + c0;
+    if (beta != 0.f) {
+      float old[8];
+      unpack8v(*reinterpret_cast<const uint4*>(q), old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(beta, old[j], v[j]);
+    }
+    *reinterpret_cast<uint4*>(q) = pack8v(v);
+  }
+}
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+}  // namespace
+
 extern "C" int iea_colsum(const void* g, int g_dtype, int g_ld, int64_t rows, int c, float* out, float beta,
                           float* scratch, iea_stream_t stream) {
   int blocks = (int)((rows + 511) / 512);
   if (blocks > 296) blocks = 296;
   if (blocks < 1) blocks = 1;
   int64_t rpb = (rows + blocks - 1) / blocks;
-  colsum_part<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, g_dtype, g_ld, rows, c, scratch, rpb);
+  if (g_dtype == IEA_BF16 && c % 8 == 0 && c <= 2048 && g_ld % 8 == 0 && al16(g)) {
+    const int lanes = 256 / (c / 8);
+    colsum_part_vec<<<blocks, 256, (size_t)lanes * c * sizeof(float), (cudaStream_t)stream>>>((const bf16*)g, g_ld, rows,
+                                                                                                 c, scratch, rpb);
+  } else {
+    colsum_part<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, g_dtype, g_ld, rows, c, scratch, rpb);
+  }
   colsum_final<<<cdiv(c, 128), 128, 0, (cudaStream_t)stream>>>(scratch, blocks, c, out, beta);
   return check_launch("iea_colsum");
 }
@@ -529,6 +612,12 @@ extern "C" int iea_residual_bwd(const void* g, int g_dtype, int g_ld, int64_t n,
                                 iea_stream_t stream) {
   int hs = res_mode == IEA_IN_UP2 ? h / 2 : (res_mode == IEA_IN_POOL2 ? h * 2 : h);
   int ws = res_mode == IEA_IN_UP2 ? w / 2 : (res_mode == IEA_IN_POOL2 ? w * 2 : w);
+  if (g_dtype == IEA_BF16 && dres_dtype == IEA_BF16 && dres_c % 8 == 0 && res_c % 8 == 0 && g_ld % 8 == 0 &&
+      dres_ld % 8 == 0 && al16(g) && al16(dres)) {
+    residual_bwd_vec<<<ew_blocks(n * hs * (int64_t)ws * (dres_c / 8)), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)g, g_ld, n, h, w, res_c, res_mode, (bf16*)dres, dres_ld, dres_c, beta);
+    return check_launch("iea_residual_bwd(vec)");
+  }
   residual_bwd_kernel<<<ew_blocks(n * hs * (int64_t)ws * dres_c), 256, 0, (cudaStream_t)stream>>>(
       g, g_dtype, g_ld, n, h, w, res_c, res_mode, dres, dres_dtype, dres_ld, dres_c, beta);
   return check_launch("iea_residual_bwd");

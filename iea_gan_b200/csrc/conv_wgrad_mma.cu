@@ -45,6 +45,7 @@ struct Params {
   float* gpart;
   int64_t M;
   int n_tiles, tiles_w, tiles_h, hs, ws, cpa, cpg, cin_eff, cout_eff, stages, depth, P, WP;
+  int nib_l, ncb_l, gi;  // output split over blockIdx.y: ci blocks / co blocks per CTA, groups along ci
   uint32_t plane_a, plane_g, stage_bytes, g_off;
 };
 
@@ -87,7 +88,9 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
   const bool thin_a = d.cin < 16, thin_g = d.cout < 16;  // 1-channel stem input / 1-channel output conv
   const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
   const int D = p.depth;
-  const int total_a = NPIX * p.cpa, total_g = 128 * p.cpg;
+  const int total_a = NPIX * p.cpa, total_g = 128 * p.cpg;            // cpa / cpg: planes staged by THIS CTA
+  const int ib0 = ((int)blockIdx.y % p.gi) * p.nib_l, cb0 = ((int)blockIdx.y / p.gi) * p.ncb_l;
+  const int ca0 = ib0 * 16, cg0 = cb0 * 16;                           // first input / output channel of this CTA
 
   float acc[NPAIR][TAPS][2][4];
 #pragma unroll
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
         const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(dst), "r"(lo), "r"(0) : "memory");
       } else {
-        const bf16* src = (const bf16*)d.x + pix * d.x_ld + c * 8;
+        const bf16* src = (const bf16*)d.x + pix * d.x_ld + ca0 + c * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       }
     }
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
           }
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3]) : "memory");
       } else {
-        const bf16* src = (const bf16*)p.g + m * p.g_ld + c * 8;
+        const bf16* src = (const bf16*)p.g + m * p.g_ld + cg0 + c * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       }
     }
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   // warp -> (output block pairs, k-step group)
-  const int nib = p.cin_eff >> 4;  // 16-wide ci blocks
+  const int nib = p.nib_l;  // 16-wide ci blocks of this CTA
   int kg = 0, pair0 = 0;
   if (p.P <= 8) { pair0 = warp % p.P; kg = warp / p.P; } else { pair0 = warp * NPAIR; }
   float sc[8], sh[8];
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
     uint8_t* sp = smem + (size_t)(it % p.stages) * p.stage_bytes;
     if (affine || relu) {  // fused prologue, in place, on the chunks this thread copied
       if (affine && o.n != ss_n) {
-        const int64_t si = (d.in_bcast ? 0 : (int64_t)o.n * d.cin) + my_c * 8;
+        const int64_t si = (d.in_bcast ? 0 : (int64_t)o.n * d.cin) + ca0 + my_c * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = d.in_scale[si + j]; sh[j] = d.in_shift[si + j]; }
         ss_n = o.n;
@@ -263,8 +266,8 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const int co = cb * 16 + (lane >> 2) + (r >= 2 ? 8 : 0);
-          const int ci = ib * 16 + j * 8 + 2 * (lane & 3) + (r & 1);
+          const int co = cg0 + cb * 16 + (lane >> 2) + (r >= 2 ? 8 : 0);
+          const int ci = ca0 + ib * 16 + j * 8 + 2 * (lane & 3) + (r & 1);
           if (co < d.cout && ci < d.cin) out[((int64_t)co * TAPS + t) * d.cin + ci] = acc[q][t][j][r];
         }
   }
@@ -295,15 +298,23 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   if (!is3 && (((int64_t)d->h * d->w) % 128) && d->in_scale) return 0;  // a tile must not straddle images
   if (!is3 && d->in_mode != IEA_IN_DIRECT) return 0;
   const int64_t M = d->n * (int64_t)d->h * d->w;
-  if (M >= (1ll << 31) || M < 128 * 64) return 0;  // small problems stay on the generic kernel
-  const int P = (cout_eff / 16) * (cin_eff / 16);
-  int npair = 1, WP = 1;
-  if (P <= 8) { if (8 % P) return 0; WP = 8 / P; }
-  else { if (P % 8) return 0; npair = P / 8; }
+  if (M >= (1ll << 31) || M < 1024) return 0;  // tiny problems stay on the generic kernel
   const int taps = d->ksize * d->ksize;
-  if (npair * taps * 8 > 160) return 0;  // accumulator registers per thread
-  if (taps == 9 ? (npair > 2) : (npair != 1 && npair != 2 && npair != 4 && npair != 8 && npair != 16)) return 0;
-  if (cin_eff / 8 > 256 || 256 % (cin_eff / 8)) return 0;
+  const int npix = is3 ? wg::PH * wg::PW : 128;
+  const uint32_t plane_a = (npix * 16 + 127) / 128 * 128, plane_g = 128 * 16;
+  // split the output blocks over blockIdx.y until the accumulators fit the registers and a stage fits smem
+  const int nib = cin_eff / 16, ncb = cout_eff / 16;
+  if ((nib & (nib - 1)) || (ncb & (ncb - 1))) return 0;
+  int nib_l = nib, ncb_l = ncb;
+  const int maxpairs = taps == 9 ? 16 : 128;
+  while (nib_l * ncb_l > maxpairs || (uint32_t)(nib_l * 2) * plane_a + (uint32_t)(ncb_l * 2) * plane_g > 80 * 1024) {
+    if (nib_l >= ncb_l && nib_l > 1) nib_l >>= 1;
+    else if (ncb_l > 1) ncb_l >>= 1;
+    else return 0;
+  }
+  const int P = nib_l * ncb_l;
+  int npair = 1, WP = 1;
+  if (P <= 8) WP = 8 / P; else npair = P / 8;
   p->d = *d;
   p->M = M;
   p->hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : d->h;
@@ -313,10 +324,10 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   p->n_tiles = (int)(is3 ? d->n * (int64_t)p->tiles_w * p->tiles_h : (M + 127) / 128);
   p->fd_tw = wg::make_fastdiv(p->tiles_w); p->fd_th = wg::make_fastdiv(p->tiles_h);
   p->fd_hw = wg::make_fastdiv(d->h * d->w);
-  p->cpa = cin_eff / 8; p->cpg = cout_eff / 8; p->cin_eff = cin_eff; p->cout_eff = cout_eff;
-  const int npix = is3 ? wg::PH * wg::PW : 128;
-  p->plane_a = (npix * 16 + 127) / 128 * 128;
-  p->plane_g = 128 * 16;
+  p->cpa = nib_l * 2; p->cpg = ncb_l * 2; p->cin_eff = cin_eff; p->cout_eff = cout_eff;
+  p->nib_l = nib_l; p->ncb_l = ncb_l; p->gi = nib / nib_l;
+  p->plane_a = plane_a;
+  p->plane_g = plane_g;
   p->g_off = p->cpa * p->plane_a;
   p->stage_bytes = p->g_off + p->cpg * p->plane_g;
   int stages = 4;
@@ -350,6 +361,7 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int taps_ = d->ksize * d->ksize;
+  const int nib_ = p.cin_eff / 16, ncb_ = p.cout_eff / 16;
   uint32_t smem = p.stages * p.stage_bytes;
   const int occ = smem <= 100 * 1024 ? 2 : 1;
   if (p.WP > 1 && smem < (uint32_t)(p.P * taps_ * 8 * 32 * 4)) smem = p.P * taps_ * 8 * 32 * 4;  // fold scratch
@@ -360,7 +372,7 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
   p.gpart = parts;
   auto launch = [&](auto kern) -> int {
     IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 256, smem, s>>>(p);
+    kern<<<dim3(grid, (nib_ / p.nib_l) * (ncb_ / p.ncb_l)), 256, smem, s>>>(p);
     return 0;
   };
   int rc = -2;
