@@ -54,6 +54,7 @@ _SIG = {
     "iea_sn_weight_bwd": [vp, i32, vp, vp, vp, vp, i32, vp, f32, i32, i32, i32, vp, vp],
     "iea_conv_fprop": [vp, vp],
     "iea_conv_tc_supported": [vp],
+    "iea_conv_stats_slots": [vp],
     "iea_conv_wgrad": [vp, vp, i32, i32, vp, i32, vp],
     "iea_conv_wgrad_mma_slices": [vp, i32, i32],
     "iea_conv_wgrad_mma": [vp, vp, i32, i32, vp, vp],

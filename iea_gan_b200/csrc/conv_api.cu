@@ -30,6 +30,19 @@ static int validate(const iea_conv_desc* d) {
   return 0;
 }
 
+int iea_conv_tc2_stats_slots(const iea_conv_desc* d);
+// batch-norm partial-sum slots per event that iea_conv_fprop will write for this descriptor
+// (0: none -- the caller runs iea_bn_stats instead).  Mirrors the dispatch below.
+extern "C" int iea_conv_stats_slots(const iea_conv_desc* d) {
+  const int64_t px = 40ll * d->h * d->w;
+  const int tiles = (d->n % 40 == 0 && px % 128 == 0) ? (int)(px / 128) : 0;
+  if (d->impl == IEA_IMPL_GENERIC) return tiles;
+  const char* v = getenv("IEA_TC_VARIANT");
+  const bool force_stream = v && v[0] == 's';
+  if ((!force_stream || !iea_conv_tc_ok(d)) && iea_conv_tc2_ok(d)) return iea_conv_tc2_stats_slots(d);
+  return tiles;
+}
+
 extern "C" int iea_conv_tc_supported(const iea_conv_desc* d) { return iea_conv_tc_ok(d) || iea_conv_tc2_ok(d); }
 
 extern "C" int iea_conv_fprop(const iea_conv_desc* d, iea_stream_t stream) {

@@ -42,7 +42,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 }
 
 struct Params {
-  FastDiv fd_tw, fd_th, fd_w, fd_h, fd_hw;
+  FastDiv fd_tw, fd_th, fd_w, fd_h, fd_hw, fd_tpe;  // fd_tpe: tiles per event (lean-epilogue statistics slots)
   iea_conv_desc d;
   const bf16* wtc;
   int64_t M;
@@ -86,7 +86,7 @@ __device__ __forceinline__ void load_ss(const iea_conv_desc& d, int64_t n, int c
   sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
 }
 
-template <int CPR, bool IS3>
+template <int CPR, bool IS3, int LEANB>
 __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(const Params p) {
   constexpr int NPIX = IS3 ? PH * PW : BM;
   constexpr int NL = (NPIX * CPR + 127) / 128;  // chunks per producer thread per patch
@@ -289,6 +289,127 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
     }
     bar_sync_epi();
     const bool need_px = IS3 || (d.res && d.res_mode != IEA_IN_DIRECT);  // (n, oh, ow) only where it is used
+    if constexpr (LEANB > 0) {
+      // ---- lean epilogue for Cout = 16 / 32 (the HBM-bound thin layers): no smem staging, no CTA
+      // barriers.  Each thread owns one output pixel: scale/bias/residual in registers, two or four
+      // 16-byte stores straight to its NHWC row, and batch-norm partial sums kept in registers ACROSS
+      // tiles; they are folded (warp shuffles + 4-warp smem) only when the CTA moves to the next event,
+      // into the slot [event][blockIdx.x][C][2] (bn_finalize then reduces gridDim.x slots per event).
+      constexpr int BN_ = 16 * LEANB;
+      float s1[BN_], s2[BN_];
+#pragma unroll
+      for (int j = 0; j < BN_; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      int cur_ev = -1;
+      float* fold = reinterpret_cast<float*>(smem + p.stat_off);  // [4 warps][2*BN_]
+      auto flush = [&](int ev) {
+#pragma unroll
+        for (int j = 0; j < BN_; ++j) {
+          s1[j] = warp_sum(s1[j]); s2[j] = warp_sum(s2[j]);
+        }
+        if (lane == 0)
+#pragma unroll
+          for (int j = 0; j < BN_; ++j) { fold[(q * BN_ + j) * 2] = s1[j]; fold[(q * BN_ + j) * 2 + 1] = s2[j]; }
+        bar_sync_epi();
+        for (int c = et; c < BN_ * 2; c += 128) {
+          const float a = fold[c] + fold[BN_ * 2 + c] + fold[2 * BN_ * 2 + c] + fold[3 * BN_ * 2 + c];
+          d.stats[((int64_t)ev * gridDim.x + blockIdx.x) * d.cout * 2 + c] = a;
+        }
+        bar_sync_epi();
+#pragma unroll
+        for (int j = 0; j < BN_; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      };
+      for (int tcount = 0; tcount < my_tiles; ++tcount) {
+        const int tile = (int)blockIdx.x + tcount * (int)gridDim.x;
+        const Origin o = tile_origin<IS3>(p, tile);
+        const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+        int64_t m; int nn = 0, oh = 0, ow = 0; bool valid = true;
+        if (IS3) {
+          nn = o.n; oh = o.h0 + (et >> 3); ow = o.w0 + (et & 7);
+          m = ((int64_t)nn * d.h + oh) * d.w + ow;
+        } else {
+          m = o.m0 + et;
+          valid = m < p.M;
+          if (valid && need_px) {
+            const unsigned mm = (unsigned)m, t = fdiv(mm, p.fd_w);
+            ow = (int)(mm - t * (unsigned)d.w); nn = (int)fdiv(t, p.fd_h); oh = (int)(t - (unsigned)nn * (unsigned)d.h);
+          }
+        }
+        if (d.stats) {
+          const int ev = (int)fdiv((unsigned)tile, p.fd_tpe);
+          if (ev != cur_ev) { if (cur_ev >= 0) flush(cur_ev); cur_ev = ev; }
+        }
+        mbar_wait(tfull_bar(ab), aph);
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < LEANB; ++cb) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.BN + cb * 16, v);
+          const int c0 = cb * 16;
+          if (valid) {  // (no early `continue`: all lanes must reconverge before the next aligned tcgen05.ld)
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
+            const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
+            v[4 * j4] = fmaf(v[4 * j4], s4.x, b4.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], s4.y, b4.y);
+            v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], s4.z, b4.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], s4.w, b4.w);
+          }
+          if (d.res && c0 < d.res_c) {
+            const bf16* rp = (const bf16*)d.res;
+            float f[16];
+            if (d.res_mode == IEA_IN_POOL2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = 0.f;
+              for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                  const bf16* sp = rp + (((int64_t)nn * (2 * d.h) + 2 * oh + a) * (2 * d.w) + 2 * ow + b) * d.res_ld + c0;
+                  float t8[16];
+                  unpack8(*reinterpret_cast<const uint4*>(sp), t8);
+                  unpack8(*reinterpret_cast<const uint4*>(sp + 8), t8 + 8);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] += 0.25f * t8[j];
+                }
+            } else {
+              const bf16* sp = d.res_mode == IEA_IN_UP2
+                                   ? rp + (((int64_t)nn * (d.h >> 1) + (oh >> 1)) * (d.w >> 1) + (ow >> 1)) * d.res_ld + c0
+                                   : rp + m * d.res_ld + c0;
+              unpack8(*reinterpret_cast<const uint4*>(sp), f);
+              unpack8(*reinterpret_cast<const uint4*>(sp + 8), f + 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += f[j];
+          }
+          uint4* yp = reinterpret_cast<uint4*>((bf16*)d.y + m * d.y_ld + c0);
+          if (d.acc_c0 >= 0 && c0 >= d.acc_c0) {
+            float f[16];
+            unpack8(yp[0], f);
+            unpack8(yp[1], f + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += f[j];
+          }
+          if (d.act == IEA_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (d.act == IEA_ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+          }
+          const uint4 lo = pack8(v), hi = pack8(v + 8);
+          yp[0] = lo;
+          yp[1] = hi;
+          if (d.stats) {  // statistics of the values as stored (bf16-rounded)
+            float r[16];
+            unpack8(lo, r);
+            unpack8(hi, r + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { s1[c0 + j] += r[j]; s2[c0 + j] = fmaf(r[j], r[j], s2[c0 + j]); }
+          }
+          }  // valid
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(ab));
+      }
+      if (d.stats && cur_ev >= 0) flush(cur_ev);
+    } else {
     const int cg = p.BN / 8;
     const bool cg_pow2 = (cg & (cg - 1)) == 0;
     const int cg_sh = 31 - __clz(cg);
@@ -422,6 +543,7 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
       }
       bar_sync_epi();  // staging / stat scratch are reused by the next tile
     }
+    }  // staged epilogue
   }
   tc_fence_before();
   __syncthreads();
@@ -445,8 +567,28 @@ int iea_conv_tc2_ok(const iea_conv_desc* d) {
   return 1;
 }
 
-int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
-  tc2::Params p;
+// tiles of one event (40 images) in this kernel's tiling; 0 when a tile could straddle two events
+static int tc2_tiles_per_event(const iea_conv_desc* d) {
+  const int64_t px = 40ll * d->h * d->w;
+  if (d->n % 40 || px % 128) return 0;
+  return (int)(px / 128);
+}
+// 0: staged epilogue; 1 / 2: lean register epilogue for Cout = 16 / 32
+int iea_conv_tc2_lean(const iea_conv_desc* d) {
+  if (d->cout != 16 && d->cout != 32) return 0;
+  if (d->y_dtype != IEA_BF16) return 0;
+  if (d->stats && !tc2_tiles_per_event(d)) return 0;
+  return d->cout / 16;
+}
+static int tc2_grid(const iea_conv_desc* d);
+// number of statistics slots per event the chosen kernel writes (engine sizes / zero-fills the buffer)
+int iea_conv_tc2_stats_slots(const iea_conv_desc* d) {
+  if (iea_conv_tc2_lean(d)) return tc2_grid(d);
+  return tc2_tiles_per_event(d);
+}
+
+// launch geometry shared by the launcher and the statistics-slot query
+static int tc2_prepare(const iea_conv_desc* d, tc2::Params& p, int& grid, uint32_t& smem_out, int& cpr_out, bool& is3_out) {
   p.d = *d;
   p.wtc = (const bf16*)d->wpack_tc;
   p.M = d->n * (int64_t)d->h * d->w;
@@ -498,15 +640,37 @@ int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int occ = (cpr <= 4 && smem <= 110 * 1024 && cols <= 256) ? 2 : 1;
   const int cap = sms * occ;
-  const int grid = p.n_tiles < cap ? p.n_tiles : cap;
+  grid = p.n_tiles < cap ? p.n_tiles : cap;
+  smem_out = smem; cpr_out = cpr; is3_out = is3;
+  return 0;
+}
+static int tc2_grid(const iea_conv_desc* d) {
+  tc2::Params p; int grid = 0, cpr; uint32_t smem; bool is3;
+  if (tc2_prepare(d, p, grid, smem, cpr, is3)) return 0;
+  return grid;
+}
+
+int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
+  tc2::Params p; int grid = 0, cpr; uint32_t smem; bool is3;
+  int rc0 = tc2_prepare(d, p, grid, smem, cpr, is3);
+  if (rc0) return rc0;
   auto launch = [&](auto kern) -> int {
     IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, tc2::THREADS, smem, s>>>(p);
     return 0;
   };
-  int rc;
-  if (is3) rc = cpr == 2 ? launch(tc2::conv_tc2_kernel<2, true>) : (cpr == 4 ? launch(tc2::conv_tc2_kernel<4, true>) : launch(tc2::conv_tc2_kernel<8, true>));
-  else rc = cpr == 2 ? launch(tc2::conv_tc2_kernel<2, false>) : (cpr == 4 ? launch(tc2::conv_tc2_kernel<4, false>) : launch(tc2::conv_tc2_kernel<8, false>));
+  const int leanb = iea_conv_tc2_lean(d);
+  const int tpe_ = tc2_tiles_per_event(d);
+  p.fd_tpe = tc2::make_fastdiv(tpe_ > 0 ? tpe_ : 1);
+  int rc = -2;
+#define IEA_TC2_LAUNCH(C_, I_, L_) if (cpr == C_ && is3 == I_ && leanb == L_) rc = launch(tc2::conv_tc2_kernel<C_, I_, L_>);
+  IEA_TC2_LAUNCH(2, true, 0) IEA_TC2_LAUNCH(2, true, 1) IEA_TC2_LAUNCH(2, true, 2)
+  IEA_TC2_LAUNCH(4, true, 0) IEA_TC2_LAUNCH(4, true, 1) IEA_TC2_LAUNCH(4, true, 2)
+  IEA_TC2_LAUNCH(8, true, 0) IEA_TC2_LAUNCH(8, true, 1) IEA_TC2_LAUNCH(8, true, 2)
+  IEA_TC2_LAUNCH(2, false, 0) IEA_TC2_LAUNCH(2, false, 1) IEA_TC2_LAUNCH(2, false, 2)
+  IEA_TC2_LAUNCH(4, false, 0) IEA_TC2_LAUNCH(4, false, 1) IEA_TC2_LAUNCH(4, false, 2)
+  IEA_TC2_LAUNCH(8, false, 0) IEA_TC2_LAUNCH(8, false, 1) IEA_TC2_LAUNCH(8, false, 2)
+#undef IEA_TC2_LAUNCH
   if (rc) return rc;
   return check_launch("iea_conv_fprop(tcgen05 resident)");
 }

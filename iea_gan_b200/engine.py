@@ -359,15 +359,19 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
         yv = out
     y = yv.t
     M = n * h * w
-    st = torch.empty((cdiv(M, 128), cout, 2), dtype=torch.float32, device=dev) if stats else None
     scale = ss.scale if ss is not None else None
     shift = ss.shift if ss is not None else None
     d = _desc(n, h, w, cin, cout, k, xv.t, xv.off(), xv.ld, in_mode, in_relu, scale, shift, wp_t, osc, oss,
-              bias, res, res_mode, res_c, acc_c0, y, yv.off(), yv.ld, act, st, wtc=wp_tc)
+              bias, res, res_mode, res_c, acc_c0, y, yv.off(), yv.ld, act, None, wtc=wp_tc)
+    st, slots = None, 0
+    if stats:  # the kernel chosen for this shape decides how many partial-sum slots per event it writes
+        d.stats = 1
+        slots = call("iea_conv_stats_slots", C.byref(d))
+        st = torch.zeros((max(n // IMGS, 1) * slots, cout, 2), dtype=torch.float32, device=dev) if slots > 0 else None
+        d.stats = ptr(st)
     K("iea_conv_fprop", C.byref(d), L.stream())
     if stats:
-        rpe = IMGS * h * w
-        yv.bn = (st, rpe // 128, rpe) if rpe % 128 == 0 else None
+        yv.bn = (st, slots, IMGS * h * w) if slots > 0 else None
     if not tape.record:
         return yv
     saved = [l.saved() for l in wls]

@@ -99,10 +99,14 @@ typedef struct {
   const void* res; int32_t res_dtype, res_ld, res_mode, res_c; /* residual for channels < res_c */
   int32_t acc_c0;                      /* channels >= acc_c0 add the existing y value; <0: off */
   void* y; int32_t y_dtype, y_ld, act;
-  float* stats;                        /* [ceil(M/128)][cout][2] or NULL, M = n*h*w */
+  float* stats;                        /* [events][iea_conv_stats_slots()][cout][2] or NULL */
   int32_t impl;                        /* iea_impl */
 } iea_conv_desc;
 int iea_conv_fprop(const iea_conv_desc* d /* host */, iea_stream_t stream);
+/* number of batch-norm partial-sum slots PER EVENT that iea_conv_fprop writes into d->stats for this
+ * descriptor (d->stats must be non-NULL when asking): the buffer is [events][slots][cout][2] floats and
+ * must be zero-filled by the caller; 0 = the kernel cannot emit statistics for this geometry. */
+int iea_conv_stats_slots(const iea_conv_desc* d /* host */);
 /* 1 if the tcgen05 path accepts this descriptor */
 int iea_conv_tc_supported(const iea_conv_desc* d /* host */);
 
