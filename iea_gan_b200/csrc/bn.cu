@@ -110,46 +110,52 @@ __global__ void bn_running_kernel(int events, double count, int c, float* stored
   if (stored_mean) { stored_mean[cc] = rm; stored_var[cc] = rv; }
 }
 
-__global__ void bn_finalize_bwd_kernel(const float* dscale, const float* dshift, const float* scale,
+// one block per channel; threads stride over the 40 images of an event (fixed-order smem reduction)
+__global__ void __launch_bounds__(64) bn_finalize_bwd_kernel(const float* dscale, const float* dshift, const float* scale,
                                        const float* mean, const float* rstd, int events, int imgs, double count,
                                        int c, const float* gain, int64_t gain_ld, float gain_add, float* dgain,
                                        int64_t dgain_ld, float* dbias, int64_t dbias_ld, int reduce_over_n,
                                        int training, float* ds1, float* ds2) {
-  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cc >= c) return;
+  __shared__ float r_m[64], r_r[64], r_g[64], r_b[64];
+  const int cc = blockIdx.x, t = threadIdx.x;
   float dg_tot = 0.f, db_tot = 0.f;
   for (int e = 0; e < events; ++e) {
     const float mu = mean[e * c + cc], rs = rstd[e * c + cc];
-    float dmean = 0.f, drstd = 0.f;
-    for (int i = 0; i < imgs; ++i) {
-      int64_t n = (int64_t)e * imgs + i;
-      float dsc = dscale[n * c + cc], dsh = dshift[n * c + cc];
-      float gn = gain_add + (gain ? gain[n * gain_ld + cc] : 0.f);
-      // scale = rstd*gn ; shift = bias - mean*scale
-      float dsc_tot = dsc - mu * dsh;          // through shift
-      float dgn = rs * dsc_tot;
+    float dmean = 0.f, drstd = 0.f, dg = 0.f, db = 0.f;
+    for (int i = t; i < imgs; i += 64) {
+      const int64_t n = (int64_t)e * imgs + i;
+      const float dsc = dscale[n * c + cc], dsh = dshift[n * c + cc];
+      const float gn = gain_add + (gain ? gain[n * gain_ld + cc] : 0.f);
+      const float dsc_tot = dsc - mu * dsh;  // scale = rstd*gn ; shift = bias - mean*scale
+      const float dgn = rs * dsc_tot;
       drstd += gn * dsc_tot;
       dmean -= dsh * scale[n * c + cc];
-      if (reduce_over_n) { dg_tot += dgn; db_tot += dsh; }
+      if (reduce_over_n) { dg += dgn; db += dsh; }
       else {
         if (dgain) dgain[n * dgain_ld + cc] = dgn;
         if (dbias) dbias[n * dbias_ld + cc] = dsh;
       }
     }
-    if (ds1) {
-      float a = 0.f, b = 0.f;
-      if (training) {
-        // rstd = (var+eps)^-1/2, var = S2/M - mean^2, mean = S1/M
-        double dvar = -0.5 * (double)drstd * (double)rs * (double)rs * (double)rs;
-        double dm = (double)dmean - 2.0 * (double)mu * dvar;
-        a = (float)(dm / count);
-        b = (float)(dvar / count);
+    r_m[t] = dmean; r_r[t] = drstd; r_g[t] = dg; r_b[t] = db;
+    __syncthreads();
+    if (t == 0) {
+      float a_m = 0.f, a_r = 0.f;
+      for (int k = 0; k < 64; ++k) { a_m += r_m[k]; a_r += r_r[k]; dg_tot += r_g[k]; db_tot += r_b[k]; }
+      if (ds1) {
+        float a = 0.f, b2 = 0.f;
+        if (training) {  // rstd = (var+eps)^-1/2, var = S2/M - mean^2, mean = S1/M
+          const double dvar = -0.5 * (double)a_r * (double)rs * (double)rs * (double)rs;
+          const double dm = (double)a_m - 2.0 * (double)mu * dvar;
+          a = (float)(dm / count);
+          b2 = (float)(dvar / count);
+        }
+        ds1[e * c + cc] = a;
+        ds2[e * c + cc] = b2;
       }
-      ds1[e * c + cc] = a;
-      ds2[e * c + cc] = b;
     }
+    __syncthreads();
   }
-  if (reduce_over_n) {
+  if (reduce_over_n && t == 0) {
     if (dgain) dgain[cc] = dg_tot;
     if (dbias) dbias[cc] = db_tot;
   }
@@ -205,7 +211,7 @@ extern "C" int iea_bn_finalize_bwd(const float* dscale, const float* dshift, con
                                    const float* gain, int64_t gain_ld, float gain_add, float* dgain, int64_t dgain_ld,
                                    float* dbias, int64_t dbias_ld, int reduce_over_n, int training, float* ds1,
                                    float* ds2, iea_stream_t stream) {
-  bn_finalize_bwd_kernel<<<cdiv(c, 64), 64, 0, (cudaStream_t)stream>>>(
+  bn_finalize_bwd_kernel<<<c, 64, 0, (cudaStream_t)stream>>>(
       dscale, dshift, scale, mean, rstd, events, imgs_per_event, (double)count_per_event, c, gain, gain_ld, gain_add,
       dgain, dgain_ld, dbias, dbias_ld, reduce_over_n, training, ds1, ds2);
   return check_launch("iea_bn_finalize_bwd");

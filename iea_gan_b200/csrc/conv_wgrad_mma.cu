@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 }
 
 struct Params {
-  FastDiv fd_tw, fd_th, fd_hw;
+  FastDiv fd_tw, fd_th, fd_hw, fd_w, fd_h;
   iea_conv_desc d;
   const void* g; int g_dtype, g_ld;
   float* gpart;
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
   const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const bool affine = d.in_scale != nullptr, relu = d.in_relu != 0;
   const bool thin_a = d.cin < 16, thin_g = d.cout < 16;  // 1-channel stem input / 1-channel output conv
+  const bool pool = d.in_mode == IEA_IN_POOL2;
   const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
   const int D = p.depth;
   const int total_a = NPIX * p.cpa, total_g = 128 * p.cpg;            // cpa / cpg: planes staged by THIS CTA
@@ -123,7 +124,34 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
       const uint32_t dst = s0 + c * p.plane_a + pp * 16;
       if (!in) { asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0) : "memory"); continue; }
       const int64_t pix = IS3 ? (((int64_t)o.n * p.hs + (ih >> sh_)) * p.ws + (iw >> sh_)) : m;
-      if (thin_a) {  // 1 input channel (fp32 or bf16): zero-extend to a 16-byte chunk
+      if (pool) {  // 1x1 conv behind AvgPool2d (DBlock conv4 / conv_sc): average of 4 transformed chunks
+        const unsigned mm = (unsigned)m, t = fdiv(mm, p.fd_w);
+        const int ow = (int)(mm - t * (unsigned)d.w), nn = (int)fdiv(t, p.fd_h), oh = (int)(t - (unsigned)nn * (unsigned)d.h);
+        float a8[8], s8[8], h8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a8[j] = 0.f; s8[j] = 1.f; h8[j] = 0.f; }
+        if (affine) {
+          const int64_t si = (d.in_bcast ? 0 : (int64_t)nn * d.cin) + ca0 + c * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s8[j] = d.in_scale[si + j]; h8[j] = d.in_shift[si + j]; }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>((const bf16*)d.x + (((int64_t)nn * p.hs + 2 * oh + a) * p.ws + 2 * ow + b) * d.x_ld + ca0 + c * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = affine ? fmaf(f[j], s8[j], h8[j]) : f[j];
+              a8[j] += relu ? fmaxf(v, 0.f) : v;
+            }
+          }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] *= 0.25f;
+        const uint4 q4 = pack8(a8);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(q4.x), "r"(q4.y), "r"(q4.z), "r"(q4.w) : "memory");
+      } else if (thin_a) {  // 1 input channel (fp32 or bf16): zero-extend to a 16-byte chunk
         const float v = c == 0 ? ld_act(d.x, d.x_dtype, pix * d.x_ld) : 0.f;
         const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(dst), "r"(lo), "r"(0) : "memory");
@@ -180,7 +208,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
     const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + it * (int)gridDim.x);
     const uint32_t s0 = sbase + (uint32_t)(it % p.stages) * p.stage_bytes;
     uint8_t* sp = smem + (size_t)(it % p.stages) * p.stage_bytes;
-    if (affine || relu) {  // fused prologue, in place, on the chunks this thread copied
+    if ((affine || relu) && !pool) {  // fused prologue, in place, on the chunks this thread copied
       if (affine && o.n != ss_n) {
         const int64_t si = (d.in_bcast ? 0 : (int64_t)o.n * d.cin) + ca0 + my_c * 8;
 #pragma unroll
@@ -291,12 +319,12 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   if (thin_a && (d->cin != 1 || d->in_scale || d->in_relu || d->in_mode != IEA_IN_DIRECT)) return 0;
   if (!thin_g && (d->cout % 16 || g_dtype != IEA_BF16 || g_ld % 8)) return 0;
   if (thin_g && d->cout > 8) return 0;
-  if (d->in_mode == IEA_IN_POOL2) return 0;
+  if (d->in_mode == IEA_IN_POOL2 && (d->ksize != 1 || thin_a)) return 0;
   const int cin_eff = thin_a ? 16 : d->cin, cout_eff = thin_g ? 16 : d->cout;
   const bool is3 = d->ksize == 3;
   if (is3 && (d->h % 16 || d->w % 8)) return 0;
   if (!is3 && (((int64_t)d->h * d->w) % 128) && d->in_scale) return 0;  // a tile must not straddle images
-  if (!is3 && d->in_mode != IEA_IN_DIRECT) return 0;
+  if (!is3 && d->in_mode == IEA_IN_UP2) return 0;
   const int64_t M = d->n * (int64_t)d->h * d->w;
   if (M >= (1ll << 31) || M < 1024) return 0;  // tiny problems stay on the generic kernel
   const int taps = d->ksize * d->ksize;
@@ -317,8 +345,9 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   if (P <= 8) WP = 8 / P; else npair = P / 8;
   p->d = *d;
   p->M = M;
-  p->hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : d->h;
-  p->ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : d->w;
+  p->hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : (d->in_mode == IEA_IN_POOL2 ? d->h * 2 : d->h);
+  p->ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : (d->in_mode == IEA_IN_POOL2 ? d->w * 2 : d->w);
+  p->fd_w = wg::make_fastdiv(d->w); p->fd_h = wg::make_fastdiv(d->h);
   p->tiles_w = is3 ? d->w / 8 : 1;
   p->tiles_h = is3 ? d->h / 16 : 1;
   p->n_tiles = (int)(is3 ? d->n * (int64_t)p->tiles_w * p->tiles_h : (M + 127) / 128);
