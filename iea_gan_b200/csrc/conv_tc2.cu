@@ -87,7 +87,7 @@ __device__ __forceinline__ void load_ss(const iea_conv_desc& d, int64_t n, int c
 }
 
 template <int CPR, bool IS3, int LEANB>
-__global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) conv_tc2_kernel(const Params p) {
   constexpr int NPIX = IS3 ? PH * PW : BM;
   constexpr int NL = (NPIX * CPR + 127) / 128;  // chunks per producer thread per patch
   extern __shared__ __align__(128) uint8_t smem[];
@@ -221,7 +221,10 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
       if (k < n_items) issue(k);
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    float sc[8], sh[8];
+    // fused prologue constants as packed bf16x2: relu(x*scale+shift) is ONE fma.rn.relu.bf16x2 per channel
+    // pair (single rounding of the fused result; scale/shift carry bf16 precision like the weights do)
+    __nv_bfloat162 sc2[4], sh2[4];
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     int ss_n = -1, ss_ci = -1;
     for (int it = 0; it < n_items; ++it) {
       if (it + D - 1 < n_items) issue(it + D - 1);
@@ -250,7 +253,16 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
       } else if (affine || relu) {  // in-place fused prologue on the chunks this thread copied
         const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + tl * (int)gridDim.x);
         const int nn = IS3 ? o.n : (int)fdiv((unsigned)o.m0, p.fd_hw);
-        if (affine && (nn != ss_n || ci != ss_ci)) { load_ss(d, nn, ci, sc, sh); ss_n = nn; ss_ci = ci; }
+        if (affine && (nn != ss_n || ci != ss_ci)) {
+          float sc[8], sh[8];
+          load_ss(d, nn, ci, sc, sh);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sc2[j] = __floats2bfloat162_rn(sc[2 * j], sc[2 * j + 1]);
+            sh2[j] = __floats2bfloat162_rn(sh[2 * j], sh[2 * j + 1]);
+          }
+          ss_n = nn; ss_ci = ci;
+        }
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
           const int pp = (i * 128 + pt) / CPR;
@@ -264,7 +276,19 @@ __global__ void __launch_bounds__(THREADS, CPR <= 4 ? 2 : 1) conv_tc2_kernel(con
           }
           if (!in) continue;  // padding stays zero
           uint4* q = reinterpret_cast<uint4*>(a0 + pp * 16);
-          *q = transform(*q, sc, sh, affine, relu);
+          uint4 v = *q;
+          __nv_bfloat162* x2 = reinterpret_cast<__nv_bfloat162*>(&v);
+          if (affine && relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x2[j] = __hfma2_relu(x2[j], sc2[j], sh2[j]);
+          } else if (affine) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x2[j] = __hfma2(x2[j], sc2[j], sh2[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x2[j] = __hmax2(x2[j], zero2);
+          }
+          *q = v;
         }
       }
       fence_async_smem();
@@ -638,7 +662,7 @@ static int tc2_prepare(const iea_conv_desc* d, tc2::Params& p, int& grid, uint32
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int occ = (cpr <= 4 && smem <= 110 * 1024 && cols <= 256) ? 2 : 1;
+  const int occ = (cpr == 2 && smem <= 72 * 1024 && cols <= 128) ? 3 : ((cpr <= 4 && smem <= 110 * 1024 && cols <= 256) ? 2 : 1);
   const int cap = sms * occ;
   grid = p.n_tiles < cap ? p.n_tiles : cap;
   smem_out = smem; cpr_out = cpr; is3_out = is3;
