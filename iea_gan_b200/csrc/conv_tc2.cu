@@ -15,6 +15,7 @@
 // has ~1400 issue slots per tile at the HBM rate, so 64-bit div/mod per chunk would dominate.
 // Layers whose weights do not fit (>= 128-channel 3x3, 512-channel 1x1) use the streaming kernel.
 #include "tc_common.cuh"
+#include <stdlib.h>
 using namespace iea;
 
 namespace tc2 {
@@ -46,7 +47,7 @@ struct Params {
   iea_conv_desc d;
   const bf16* wtc;
   int64_t M;
-  int n_tiles, hw, hs, ws, KB, nkb, BN, taps, tiles_w, tiles_h, npix, stages, uniform_n, depth;
+  int n_tiles, hw, hs, ws, KB, nkb, BN, taps, tiles_w, tiles_h, npix, stages, uniform_n, depth, dbg;
   uint32_t plane, stage_bytes, w_bytes, stage_off, staging_off, staging_ld, stat_off, bar_off, tmem_cols;
 };
 
@@ -117,7 +118,11 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // blocked tile partition: each CTA owns a contiguous run of tiles, so consecutive tiles share the image
+  // (per-image scale/shift stay in registers), halos hit L1/L2 and the event-boundary flushes are rare
+  const int t_base = p.n_tiles / (int)gridDim.x, t_rem = p.n_tiles % (int)gridDim.x;
+  const int my_tiles = t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
+  const int tile0 = (int)blockIdx.x * t_base + ((int)blockIdx.x < t_rem ? (int)blockIdx.x : t_rem);
 
   if (warp == 0) {
     // ===================== weight TMA + MMA issuer =====================
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
             for (int j = 0; j < CPR / 2; ++j) {
               const uint64_t da = make_desc(a_tap + 2 * j * p.plane, p.plane, sbo_a);
               const uint64_t db = make_desc(b_tap + 2 * j * lbo_b, lbo_b, 128);
-              tc_mma(tacc, da, db, idesc, (kb > 0 || tap > 0 || j > 0) ? 1u : 0u);
+              if (!(p.dbg & 2)) tc_mma(tacc, da, db, idesc, (kb > 0 || tap > 0 || j > 0) ? 1u : 0u);
             }
           }
           tc_commit(empty_bar(s));
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
       const uint32_t s = (uint32_t)(it % p.stages), ph = (uint32_t)((it / p.stages) & 1);
       mbar_wait(empty_bar(s), ph ^ 1);
       if (slow) return;
-      const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + tl * (int)gridDim.x);
+      const Origin o = tile_origin<IS3>(p, tile0 + tl);
       const uint32_t a0 = sbase + p.stage_off + s * p.stage_bytes + cc * p.plane;
       const int ci = kb * p.KB + cc * 8;
 #pragma unroll
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
           const float v = cc == 0 ? ld_act(d.x, d.x_dtype, pix * d.x_ld) : 0.f;
           const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(a0 + pp * 16), "r"(lo), "r"(0) : "memory");
-        } else if (in) {
+        } else if (in && !(p.dbg & 16)) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a0 + pp * 16), "l"(xb + pix * d.x_ld + ci) : "memory");
         } else {
           asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a0 + pp * 16), "r"(0) : "memory");
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
       uint8_t* a0 = smem + p.stage_off + s * p.stage_bytes + cc * p.plane;
       const int ci = kb * p.KB + cc * 8;
       if (slow) {
-        const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + tl * (int)gridDim.x);
+        const Origin o = tile_origin<IS3>(p, tile0 + tl);
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
           const int pp = (i * 128 + pt) / CPR;
@@ -250,8 +255,8 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
           const bool in = coords_slow(o, pp, nn, ih, iw);
           *reinterpret_cast<uint4*>(a0 + pp * 16) = in ? load_chunk(d, p.hs, p.ws, nn, ih, iw, ci) : make_uint4(0, 0, 0, 0);
         }
-      } else if (affine || relu) {  // in-place fused prologue on the chunks this thread copied
-        const Origin o = tile_origin<IS3>(p, (int)blockIdx.x + tl * (int)gridDim.x);
+      } else if ((affine || relu) && !(p.dbg & 1)) {  // in-place fused prologue on the chunks this thread copied
+        const Origin o = tile_origin<IS3>(p, tile0 + tl);
         const int nn = IS3 ? o.n : (int)fdiv((unsigned)o.m0, p.fd_hw);
         if (affine && (nn != ss_n || ci != ss_ci)) {
           float sc[8], sh[8];
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
         for (int j = 0; j < BN_; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
       };
       for (int tcount = 0; tcount < my_tiles; ++tcount) {
-        const int tile = (int)blockIdx.x + tcount * (int)gridDim.x;
+        const int tile = tile0 + tcount;
         const Origin o = tile_origin<IS3>(p, tile);
         const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
         int64_t m; int nn = 0, oh = 0, ow = 0; bool valid = true;
@@ -418,9 +423,8 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
             for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
           }
           const uint4 lo = pack8(v), hi = pack8(v + 8);
-          yp[0] = lo;
-          yp[1] = hi;
-          if (d.stats) {  // statistics of the values as stored (bf16-rounded)
+          if (!(p.dbg & 4)) { yp[0] = lo; yp[1] = hi; }
+          if (d.stats && !(p.dbg & 8)) {  // statistics of the values as stored (bf16-rounded)
             float r[16];
             unpack8(lo, r);
             unpack8(hi, r + 8);
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
     while (parts * 2 * cg <= 128) parts *= 2;
     const int rows_per = BM / parts;
     for (int tcount = 0; tcount < my_tiles; ++tcount) {
-      const int tile = (int)blockIdx.x + tcount * (int)gridDim.x;
+      const int tile = tile0 + tcount;
       const Origin o = tile_origin<IS3>(p, tile);
       const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
       // this thread's output pixel
@@ -615,6 +619,7 @@ int iea_conv_tc2_stats_slots(const iea_conv_desc* d) {
 static int tc2_prepare(const iea_conv_desc* d, tc2::Params& p, int& grid, uint32_t& smem_out, int& cpr_out, bool& is3_out) {
   p.d = *d;
   p.wtc = (const bf16*)d->wpack_tc;
+  { const char* e_ = getenv("IEA_TC2_DBG"); p.dbg = e_ ? atoi(e_) : 0; }  // profiling ablations only
   p.M = d->n * (int64_t)d->h * d->w;
   p.hw = d->h * d->w;
   p.fd_w = tc2::make_fastdiv(d->w); p.fd_h = tc2::make_fastdiv(d->h); p.fd_hw = tc2::make_fastdiv(p.hw);

@@ -5,7 +5,7 @@
 
 namespace tc {
 using namespace iea;
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
+constexpr uint32_t SPIN_LIMIT = 1u << 20;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -18,15 +18,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the
+  // hint expires), so a waiting role issues almost no instructions.  A plain poll loop costs thousands of
+  // issue slots per tile here because every role spends most of its time waiting on another one.
   uint32_t ok = 0;
+#pragma unroll 1
   for (uint32_t i = 0; i < SPIN_LIMIT; ++i) {
     asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return;
-    if (i > 2) __nanosleep(40);  // back off: spinning warps steal issue slots from the working roles
   }
   __trap();  // a pipeline bug must never hang the GPU
 }
