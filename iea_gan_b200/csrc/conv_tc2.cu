@@ -42,12 +42,20 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
   return (t + ((n - t) >> 1)) >> (f.shr - 1);
 }
 
+#ifdef IEA_TC2_TRACE
+// pipeline trace of CTA 0 (profiling builds only): clock64 stamps per role and item
+__device__ long long g_trace[8][512];
+#define TRACE(slot, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_trace[slot][idx] = clock64(); } while (0)
+#else
+#define TRACE(slot, idx) do { } while (0)
+#endif
+
 struct Params {
   FastDiv fd_tw, fd_th, fd_w, fd_h, fd_hw, fd_tpe;  // fd_tpe: tiles per event (lean-epilogue statistics slots)
   iea_conv_desc d;
   const bf16* wtc;
   int64_t M;
-  int n_tiles, hw, hs, ws, KB, nkb, BN, taps, tiles_w, tiles_h, npix, stages, uniform_n, depth, dbg;
+  int n_tiles, hw, hs, ws, KB, nkb, BN, taps, tiles_w, tiles_h, npix, stages, uniform_n, depth, dbg, occ;
   uint32_t plane, stage_bytes, w_bytes, stage_off, staging_off, staging_ld, stat_off, bar_off, tmem_cols;
 };
 
@@ -68,6 +76,44 @@ __device__ __forceinline__ Origin tile_origin(const Params& p, int tile) {
   return o;
 }
 
+// (image, tile row, tile column) of a tile, advanced without divisions.  1x1 layers use tiles_h = 1 and
+// tiles_w = tiles per image (or "never wraps" when an image is not a whole number of tiles).
+struct TilePos { int n, th, tw; };
+__device__ __forceinline__ TilePos tile_pos(const Params& p, int tile) {
+  TilePos c;
+  const unsigned t = fdiv((unsigned)tile, p.fd_tw);
+  c.tw = (int)((unsigned)tile - t * (unsigned)p.tiles_w);
+  c.n = (int)fdiv(t, p.fd_th);
+  c.th = (int)(t - (unsigned)c.n * (unsigned)p.tiles_h);
+  return c;
+}
+__device__ __forceinline__ void tile_next(const Params& p, TilePos& c) {
+  if (++c.tw == p.tiles_w) { c.tw = 0; if (++c.th == p.tiles_h) { c.th = 0; ++c.n; } }
+}
+template <bool IS3>
+__device__ __forceinline__ Origin origin_of(const TilePos& c, int tile) {
+  Origin o;
+  if (IS3) { o.n = c.n; o.h0 = c.th * 16; o.w0 = c.tw * 8; o.m0 = 0; }
+  else { o.m0 = (int64_t)tile * BM; o.n = 0; o.h0 = 0; o.w0 = 0; }
+  return o;
+}
+
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): half the issue slots of scalar fp32 in the epilogue
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return r;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return r;
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
+
 __device__ __forceinline__ uint4 transform(const uint4& raw, const float* sc, const float* sh, bool affine, bool relu) {
   float f[8];
   unpack8(raw, f);
@@ -87,10 +133,12 @@ __device__ __forceinline__ void load_ss(const iea_conv_desc& d, int64_t n, int c
   sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
 }
 
-template <int CPR, bool IS3, int LEANB>
-__global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) conv_tc2_kernel(const Params p) {
+template <int CPR, bool IS3, int LEANB, int OCC>
+__global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) {
   constexpr int NPIX = IS3 ? PH * PW : BM;
   constexpr int NL = (NPIX * CPR + 127) / 128;  // chunks per producer thread per patch
+  constexpr int TAPS = IS3 ? 9 : 1;
+  constexpr int GP = 128 / CPR;                 // patch pixels covered by one pass of the 128 producer threads
   extern __shared__ __align__(128) uint8_t smem[];
   const iea_conv_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -136,46 +184,83 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t lbo_b = p.BN * 16;
       const uint32_t sbo_a = IS3 ? PW * 16 : 128;
-      uint32_t g = 0;
+      // descriptors differ only in their 16-byte-unit start address: build the two bases once and add offsets
+      const uint64_t da_base = make_desc(sbase + p.stage_off, p.plane, sbo_a);
+      const uint64_t db_base = make_desc(sbase, lbo_b, 128);
+      const uint32_t stage16 = p.stage_bytes >> 4, plane16 = p.plane >> 4, lbo16 = lbo_b >> 4;
+      uint32_t s = 0, ph = 0;
       for (int tcount = 0; tcount < my_tiles; ++tcount) {
         const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(tempty_bar(ab), aph ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + ab * p.BN;
-        for (int kb = 0; kb < p.nkb; ++kb, ++g) {
-          const uint32_t s = g % p.stages, ph = (g / p.stages) & 1;
+        for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t a0 = sbase + p.stage_off + s * p.stage_bytes;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const uint32_t a_tap = a0 + (IS3 ? ((tap / 3) * PW + (tap % 3)) * 16 : 0);
-            const uint32_t b_tap = sbase + ((uint32_t)(tap * p.nkb + kb) * CPR) * lbo_b;
+          TRACE(3, tcount);
+          const uint32_t a16 = s * stage16;
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const uint32_t a_tap = a16 + (IS3 ? (tap / 3) * PW + (tap % 3) : 0);
+            const uint32_t b_tap = (uint32_t)(tap * p.nkb + kb) * CPR * lbo16;
 #pragma unroll
             for (int j = 0; j < CPR / 2; ++j) {
-              const uint64_t da = make_desc(a_tap + 2 * j * p.plane, p.plane, sbo_a);
-              const uint64_t db = make_desc(b_tap + 2 * j * lbo_b, lbo_b, 128);
+              const uint64_t da = da_base + (a_tap + 2 * j * plane16);
+              const uint64_t db = db_base + (b_tap + 2 * j * lbo16);
               if (!(p.dbg & 2)) tc_mma(tacc, da, db, idesc, (kb > 0 || tap > 0 || j > 0) ? 1u : 0u);
             }
           }
           tc_commit(empty_bar(s));
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
         }
         tc_commit(tfull_bar(ab));
+        TRACE(4, tcount);
       }
     }
   } else if (warp <= 4) {
     // ===================== patch producers =====================
     const int pt = tid - 32;
-    const int cc = pt % CPR;
+    const int cc = pt % CPR, pp0 = pt / CPR;
     const bool affine = d.in_scale != nullptr;
     const bool relu = d.in_relu != 0;
     const bool pool = d.in_mode == IEA_IN_POOL2;
     const bool thin_a = d.cin < 16;                             // 1-channel image (D stem): zero-extended chunks
     const bool flat = !IS3 && d.in_mode == IEA_IN_DIRECT;      // 1x1 on a same-resolution input: pixel index == row
     const bool slow = pool || (affine && !p.uniform_n) || (!IS3 && !flat);  // rare shapes: per-chunk generic path
+    const bool fast = !slow && !thin_a;                         // interior tiles: precomputed chunk offsets
     const int D = p.depth;                                       // patches kept in flight by cp.async
     const int n_items = my_tiles * p.nkb;
     const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
     const bf16* xb = (const bf16*)d.x;
+
+    // Tile-independent part of this thread's chunk addresses.  Slot i of a patch is pixel pp = i*GP + pp0,
+    // chunk cc; its global element offset from the tile's base pixel and its smem offset never change, so an
+    // interior tile costs one 64-bit add + one cp.async per chunk (nearest-up2 is folded into the offsets:
+    // tile origins are even, hence (h0 - 1 + pi) >> 1 == h0/2 + ((pi - 1) >> 1)).
+    int dlt[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int pp = i * GP + pp0;
+      if (IS3) {
+        const int pi = pp / PW, pj = pp - pi * PW;
+        dlt[i] = (((pi - 1) >> sh_) * p.ws + ((pj - 1) >> sh_)) * d.x_ld;
+      } else {
+        dlt[i] = pp * d.x_ld;
+      }
+    }
+    const bool last_ok = (NL - 1) * GP + pp0 < NPIX;
+    const uint32_t a_thr = sbase + p.stage_off + cc * p.plane + pp0 * 16;  // + stage offset + i*GP*16
+
+    // position of a pipeline item (tile, k block) and of its ring slot
+    struct Cur { int tl, kb; uint32_t s, ph; TilePos t; };
+    auto cur_next = [&](Cur& c) {
+      if (++c.s == (uint32_t)p.stages) { c.s = 0; c.ph ^= 1; }
+      if (++c.kb == p.nkb) { c.kb = 0; ++c.tl; tile_next(p, c.t); }
+    };
+    auto interior_of = [&](const Cur& c) -> bool {
+      if (IS3) return c.t.th > 0 && c.t.th < p.tiles_h - 1 && c.t.tw > 0 && c.t.tw < p.tiles_w - 1;
+      return (int64_t)(tile0 + c.tl + 1) * BM <= p.M;
+    };
 
     // generic (slow-path) coordinates of patch pixel pp
     auto coords_slow = [&](const Origin& o, int pp, int64_t& nn, int& ih, int& iw) -> bool {
@@ -187,18 +272,29 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
       }
       return (unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w;
     };
-    // asynchronous copy of this thread's raw chunks of item `it` straight into their final smem slots
-    auto issue = [&](int it) {
-      const int tl = it / p.nkb, kb = it - tl * p.nkb;
-      const uint32_t s = (uint32_t)(it % p.stages), ph = (uint32_t)((it / p.stages) & 1);
-      mbar_wait(empty_bar(s), ph ^ 1);
+    // asynchronous copy of this thread's raw chunks of item `c` straight into their final smem slots
+    auto issue = [&](const Cur& c) {
+      mbar_wait(empty_bar(c.s), c.ph ^ 1);
       if (slow) return;
-      const Origin o = tile_origin<IS3>(p, tile0 + tl);
-      const uint32_t a0 = sbase + p.stage_off + s * p.stage_bytes + cc * p.plane;
-      const int ci = kb * p.KB + cc * 8;
+      const int ci = c.kb * p.KB + cc * 8;
+      const uint32_t a1 = a_thr + c.s * p.stage_bytes;
+      if (fast && interior_of(c)) {
+        int64_t base;
+        if (IS3) base = ((int64_t)(c.t.n * p.hs + ((c.t.th * 16) >> sh_)) * p.ws + ((c.t.tw * 8) >> sh_)) * d.x_ld + ci;
+        else base = (int64_t)(tile0 + c.tl) * BM * d.x_ld + ci;
+        const bf16* bp = xb + base;
+        if (!(p.dbg & 16)) {
+#pragma unroll
+          for (int i = 0; i < NL; ++i)
+            if (i < NL - 1 || last_ok)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a1 + i * GP * 16), "l"(bp + dlt[i]) : "memory");
+        }
+        return;
+      }
+      const Origin o = origin_of<IS3>(c.t, tile0 + c.tl);
 #pragma unroll
       for (int i = 0; i < NL; ++i) {
-        const int pp = (i * 128 + pt) / CPR;
+        const int pp = i * GP + pp0;
         if (pp >= NPIX) continue;
         int64_t pix;
         bool in;
@@ -213,17 +309,21 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
         if (in && thin_a) {
           const float v = cc == 0 ? ld_act(d.x, d.x_dtype, pix * d.x_ld) : 0.f;
           const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(a0 + pp * 16), "r"(lo), "r"(0) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(a1 + i * GP * 16), "r"(lo), "r"(0) : "memory");
         } else if (in && !(p.dbg & 16)) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a0 + pp * 16), "l"(xb + pix * d.x_ld + ci) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a1 + i * GP * 16), "l"(xb + pix * d.x_ld + ci) : "memory");
         } else {
-          asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a0 + pp * 16), "r"(0) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a1 + i * GP * 16), "r"(0) : "memory");
         }
       }
     };
 
+    Cur ci_, ct_;  // issue cursor (runs D-1 items ahead) and transform cursor
+    ci_.tl = 0; ci_.kb = 0; ci_.s = 0; ci_.ph = 0; ci_.t = tile_pos(p, tile0);
+    ct_ = ci_;
+    int issued = 0;
     for (int k = 0; k < D - 1; ++k) {
-      if (k < n_items) issue(k);
+      if (issued < n_items) { issue(ci_); cur_next(ci_); ++issued; }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // fused prologue constants as packed bf16x2: relu(x*scale+shift) is ONE fma.rn.relu.bf16x2 per channel
@@ -232,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     int ss_n = -1, ss_ci = -1;
     for (int it = 0; it < n_items; ++it) {
-      if (it + D - 1 < n_items) issue(it + D - 1);
+      if (issued < n_items) { issue(ci_); cur_next(ci_); ++issued; }
       asm volatile("cp.async.commit_group;" ::: "memory");
       switch (D) {  // wait until item `it` (this thread's part) has landed
         case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
@@ -241,23 +341,22 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
         case 6: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
         default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
       }
-      const int tl = it / p.nkb, kb = it - tl * p.nkb;
-      const uint32_t s = (uint32_t)(it % p.stages);
-      uint8_t* a0 = smem + p.stage_off + s * p.stage_bytes + cc * p.plane;
-      const int ci = kb * p.KB + cc * 8;
+      if (pt == 0) TRACE(0, it);
+      const Cur& c = ct_;
+      const int ci = c.kb * p.KB + cc * 8;
+      uint8_t* a1 = smem + (a_thr - sbase) + c.s * p.stage_bytes;
       if (slow) {
-        const Origin o = tile_origin<IS3>(p, tile0 + tl);
+        const Origin o = origin_of<IS3>(c.t, tile0 + c.tl);
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
-          const int pp = (i * 128 + pt) / CPR;
+          const int pp = i * GP + pp0;
           if (pp >= NPIX) continue;
           int64_t nn; int ih, iw;
           const bool in = coords_slow(o, pp, nn, ih, iw);
-          *reinterpret_cast<uint4*>(a0 + pp * 16) = in ? load_chunk(d, p.hs, p.ws, nn, ih, iw, ci) : make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(a1 + i * GP * 16) = in ? load_chunk(d, p.hs, p.ws, nn, ih, iw, ci) : make_uint4(0, 0, 0, 0);
         }
       } else if ((affine || relu) && !(p.dbg & 1)) {  // in-place fused prologue on the chunks this thread copied
-        const Origin o = tile_origin<IS3>(p, tile0 + tl);
-        const int nn = IS3 ? o.n : (int)fdiv((unsigned)o.m0, p.fd_hw);
+        const int nn = c.t.n;  // (affine on a 1x1 layer implies uniform_n, so the cursor's image index is exact)
         if (affine && (nn != ss_n || ci != ss_ci)) {
           float sc[8], sh[8];
           load_ss(d, nn, ci, sc, sh);
@@ -268,19 +367,23 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
           }
           ss_n = nn; ss_ci = ci;
         }
+        const bool inter = fast && interior_of(c);
+        const Origin o = origin_of<IS3>(c.t, tile0 + c.tl);
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
-          const int pp = (i * 128 + pt) / CPR;
-          if (pp >= NPIX) continue;
-          bool in;
-          if (IS3) {
-            const int pi = pp / PW, ih = o.h0 - 1 + pi, iw = o.w0 - 1 + (pp - pi * PW);
-            in = (unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w;
-          } else {
-            in = o.m0 + pp < p.M;
+          if (i == NL - 1 && !last_ok) continue;
+          if (!inter) {  // border tile: padding pixels stay zero
+            const int pp = i * GP + pp0;
+            bool in;
+            if (IS3) {
+              const int pi = pp / PW, ih = o.h0 - 1 + pi, iw = o.w0 - 1 + (pp - pi * PW);
+              in = (unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w;
+            } else {
+              in = o.m0 + pp < p.M;
+            }
+            if (!in) continue;
           }
-          if (!in) continue;  // padding stays zero
-          uint4* q = reinterpret_cast<uint4*>(a0 + pp * 16);
+          uint4* q = reinterpret_cast<uint4*>(a1 + i * GP * 16);
           uint4 v = *q;
           __nv_bfloat162* x2 = reinterpret_cast<__nv_bfloat162*>(&v);
           if (affine && relu) {
@@ -296,8 +399,11 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
           *q = v;
         }
       }
+      if (pt == 0) TRACE(1, it);
       fence_async_smem();
-      mbar_arrive(full_bar(s));
+      mbar_arrive(full_bar(c.s));
+      if (pt == 0) TRACE(2, it);
+      cur_next(ct_);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
@@ -325,19 +431,24 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
       // tiles; they are folded (warp shuffles + 4-warp smem) only when the CTA moves to the next event,
       // into the slot [event][blockIdx.x][C][2] (bn_finalize then reduces gridDim.x slots per event).
       constexpr int BN_ = 16 * LEANB;
-      float s1[BN_], s2[BN_];
+      // (the sums are taken on the fp32 values before the bf16 rounding of the store: the rounding error is
+      // zero-mean and 2^-9 relative, far below the batch statistics' own noise; it saves the unpack)
+      float2 s1[BN_ / 2], s2[BN_ / 2];
 #pragma unroll
-      for (int j = 0; j < BN_; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-      int cur_ev = -1;
+      for (int j = 0; j < BN_ / 2; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = s1[j]; }
       float* fold = reinterpret_cast<float*>(smem + p.stat_off);  // [4 warps][2*BN_]
       auto flush = [&](int ev) {
 #pragma unroll
-        for (int j = 0; j < BN_; ++j) {
-          s1[j] = warp_sum(s1[j]); s2[j] = warp_sum(s2[j]);
+        for (int j = 0; j < BN_ / 2; ++j) {
+          s1[j].x = warp_sum(s1[j].x); s1[j].y = warp_sum(s1[j].y);
+          s2[j].x = warp_sum(s2[j].x); s2[j].y = warp_sum(s2[j].y);
         }
         if (lane == 0)
 #pragma unroll
-          for (int j = 0; j < BN_; ++j) { fold[(q * BN_ + j) * 2] = s1[j]; fold[(q * BN_ + j) * 2 + 1] = s2[j]; }
+          for (int j = 0; j < BN_ / 2; ++j) {
+            fold[(q * BN_ + 2 * j) * 2] = s1[j].x; fold[(q * BN_ + 2 * j) * 2 + 1] = s2[j].x;
+            fold[(q * BN_ + 2 * j + 1) * 2] = s1[j].y; fold[(q * BN_ + 2 * j + 1) * 2 + 1] = s2[j].y;
+          }
         bar_sync_epi();
         for (int c = et; c < BN_ * 2; c += 128) {
           const float a = fold[c] + fold[BN_ * 2 + c] + fold[2 * BN_ * 2 + c] + fold[3 * BN_ * 2 + c];
@@ -345,98 +456,109 @@ __global__ void __launch_bounds__(THREADS, CPR == 2 ? 3 : (CPR == 4 ? 2 : 1)) co
         }
         bar_sync_epi();
 #pragma unroll
-        for (int j = 0; j < BN_; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        for (int j = 0; j < BN_ / 2; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = s1[j]; }
       };
+      const bool has_sb = d.out_scale != nullptr || d.bias != nullptr;
+      const bool has_stats = d.stats != nullptr;
+      const int tpe = (int)p.fd_tpe.d;                     // tiles per event (statistics are per event)
+      int ev = (int)fdiv((unsigned)tile0, p.fd_tpe), ev_pos = tile0 - ev * tpe;
+      TilePos tp = tile_pos(p, tile0);
+      const int er = et >> 3, ec = et & 7;
+      bf16* const yb = (bf16*)d.y;
       for (int tcount = 0; tcount < my_tiles; ++tcount) {
-        const int tile = tile0 + tcount;
-        const Origin o = tile_origin<IS3>(p, tile);
         const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
-        int64_t m; int nn = 0, oh = 0, ow = 0; bool valid = true;
+        int m; int nn = 0, oh = 0, ow = 0; bool valid = true;  // (M < 2^31 is checked on the host)
         if (IS3) {
-          nn = o.n; oh = o.h0 + (et >> 3); ow = o.w0 + (et & 7);
-          m = ((int64_t)nn * d.h + oh) * d.w + ow;
+          nn = tp.n; oh = tp.th * 16 + er; ow = tp.tw * 8 + ec;
+          m = (nn * d.h + oh) * d.w + ow;
         } else {
-          m = o.m0 + et;
+          m = (tile0 + tcount) * BM + et;
           valid = m < p.M;
           if (valid && need_px) {
             const unsigned mm = (unsigned)m, t = fdiv(mm, p.fd_w);
             ow = (int)(mm - t * (unsigned)d.w); nn = (int)fdiv(t, p.fd_h); oh = (int)(t - (unsigned)nn * (unsigned)d.h);
           }
         }
-        if (d.stats) {
-          const int ev = (int)fdiv((unsigned)tile, p.fd_tpe);
-          if (ev != cur_ev) { if (cur_ev >= 0) flush(cur_ev); cur_ev = ev; }
+        tile_next(p, tp);
+        if (has_stats) {
+          if (ev_pos == tpe) { flush(ev); ++ev; ev_pos = 0; }
+          ++ev_pos;
         }
+        if (et == 0) TRACE(5, tcount);
         mbar_wait(tfull_bar(ab), aph);
         tc_fence_after();
+        if (et == 0) TRACE(6, tcount);
 #pragma unroll
         for (int cb = 0; cb < LEANB; ++cb) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.BN + cb * 16, v);
+          float2 v[8];
+          {
+            float t16[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.BN + cb * 16, t16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = make_float2(t16[2 * j], t16[2 * j + 1]);
+          }
           const int c0 = cb * 16;
           if (valid) {  // (no early `continue`: all lanes must reconverge before the next aligned tcgen05.ld)
+          if (has_sb) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
-            const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
-            v[4 * j4] = fmaf(v[4 * j4], s4.x, b4.x); v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], s4.y, b4.y);
-            v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], s4.z, b4.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], s4.w, b4.w);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
+              const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
+              v[2 * j4] = ffma2(v[2 * j4], make_float2(s4.x, s4.y), make_float2(b4.x, b4.y));
+              v[2 * j4 + 1] = ffma2(v[2 * j4 + 1], make_float2(s4.z, s4.w), make_float2(b4.z, b4.w));
+            }
           }
           if (d.res && c0 < d.res_c) {
             const bf16* rp = (const bf16*)d.res;
-            float f[16];
             if (d.res_mode == IEA_IN_POOL2) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = 0.f;
+              const float2 quarter = make_float2(0.25f, 0.25f);
               for (int a = 0; a < 2; ++a)
                 for (int b = 0; b < 2; ++b) {
                   const bf16* sp = rp + (((int64_t)nn * (2 * d.h) + 2 * oh + a) * (2 * d.w) + 2 * ow + b) * d.res_ld + c0;
-                  float t8[16];
-                  unpack8(*reinterpret_cast<const uint4*>(sp), t8);
-                  unpack8(*reinterpret_cast<const uint4*>(sp + 8), t8 + 8);
+                  const uint4 r0 = *reinterpret_cast<const uint4*>(sp), r1 = *reinterpret_cast<const uint4*>(sp + 8);
+                  const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) f[j] += 0.25f * t8[j];
+                  for (int j = 0; j < 8; ++j) v[j] = ffma2(bf2_to_f2(w[j]), quarter, v[j]);
                 }
             } else {
               const bf16* sp = d.res_mode == IEA_IN_UP2
                                    ? rp + (((int64_t)nn * (d.h >> 1) + (oh >> 1)) * (d.w >> 1) + (ow >> 1)) * d.res_ld + c0
-                                   : rp + m * d.res_ld + c0;
-              unpack8(*reinterpret_cast<const uint4*>(sp), f);
-              unpack8(*reinterpret_cast<const uint4*>(sp + 8), f + 8);
+                                   : rp + (int64_t)m * d.res_ld + c0;
+              const uint4 r0 = *reinterpret_cast<const uint4*>(sp), r1 = *reinterpret_cast<const uint4*>(sp + 8);
+              const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += f[j];
           }
-          uint4* yp = reinterpret_cast<uint4*>((bf16*)d.y + m * d.y_ld + c0);
+          uint4* yp = reinterpret_cast<uint4*>(yb + (int64_t)m * d.y_ld + c0);
           if (d.acc_c0 >= 0 && c0 >= d.acc_c0) {
-            float f[16];
-            unpack8(yp[0], f);
-            unpack8(yp[1], f + 8);
+            const uint4 r0 = yp[0], r1 = yp[1];
+            const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += f[j];
+            for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
           }
           if (d.act == IEA_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 8; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); }
           } else if (d.act == IEA_ACT_TANH) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+            for (int j = 0; j < 8; ++j) { v[j].x = tanhf(v[j].x); v[j].y = tanhf(v[j].y); }
           }
-          const uint4 lo = pack8(v), hi = pack8(v + 8);
-          if (!(p.dbg & 4)) { yp[0] = lo; yp[1] = hi; }
-          if (d.stats && !(p.dbg & 8)) {  // statistics of the values as stored (bf16-rounded)
-            float r[16];
-            unpack8(lo, r);
-            unpack8(hi, r + 8);
+          uint32_t o[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { s1[c0 + j] += r[j]; s2[c0 + j] = fmaf(r[j], r[j], s2[c0 + j]); }
+          for (int j = 0; j < 8; ++j) o[j] = pack2(v[j].x, v[j].y);
+          if (!(p.dbg & 4)) { yp[0] = make_uint4(o[0], o[1], o[2], o[3]); yp[1] = make_uint4(o[4], o[5], o[6], o[7]); }
+          if (has_stats && !(p.dbg & 8)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[cb * 8 + j] = fadd2(s1[cb * 8 + j], v[j]); s2[cb * 8 + j] = ffma2(v[j], v[j], s2[cb * 8 + j]); }
           }
           }  // valid
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(ab));
+        if (et == 0) TRACE(7, tcount);
       }
-      if (d.stats && cur_ev >= 0) flush(cur_ev);
+      if (has_stats && my_tiles > 0) flush(ev);
     } else {
     const int cg = p.BN / 8;
     const bool cg_pow2 = (cg & (cg - 1)) == 0;
@@ -631,12 +753,13 @@ static int tc2_prepare(const iea_conv_desc* d, tc2::Params& p, int& grid, uint32
   p.taps = d->ksize * d->ksize;
   p.BN = d->cout < 16 ? 16 : d->cout;
   const bool is3 = d->ksize == 3;
-  p.tiles_w = is3 ? d->w / 8 : 1;
+  p.uniform_n = is3 ? 1 : (((int64_t)d->h * d->w) % 128 == 0 ? 1 : 0);
+  p.n_tiles = (int)(is3 ? d->n * (int64_t)(d->w / 8) * (d->h / 16) : (p.M + 127) / 128);
+  // 1x1: a "tile row" is one image when images are whole tiles; otherwise the column counter never wraps
+  p.tiles_w = is3 ? d->w / 8 : (p.uniform_n ? p.hw / 128 : p.n_tiles + 1);
   p.tiles_h = is3 ? d->h / 16 : 1;
-  p.n_tiles = (int)(is3 ? d->n * (int64_t)p.tiles_w * p.tiles_h : (p.M + 127) / 128);
   p.fd_tw = tc2::make_fastdiv(p.tiles_w); p.fd_th = tc2::make_fastdiv(p.tiles_h);
   p.npix = is3 ? tc2::PH * tc2::PW : 128;
-  p.uniform_n = is3 ? 1 : (((int64_t)d->h * d->w) % 128 == 0 ? 1 : 0);
   const int cpr = p.KB / 8;
   p.plane = (p.npix * 16 + 127) / 128 * 128 + (cpr == 8 ? 64 : 0);
   p.stage_bytes = (cpr * p.plane + 127) / 128 * 128;
@@ -667,7 +790,9 @@ static int tc2_prepare(const iea_conv_desc* d, tc2::Params& p, int& grid, uint32
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int occ = (cpr == 2 && smem <= 72 * 1024 && cols <= 128) ? 3 : ((cpr <= 4 && smem <= 110 * 1024 && cols <= 256) ? 2 : 1);
+  int occ = (cpr == 2 && smem <= 72 * 1024 && cols <= 128) ? 3 : ((cpr <= 4 && smem <= 110 * 1024 && cols <= 256) ? 2 : 1);
+  { const char* e_ = getenv("IEA_TC2_OCC"); if (e_ && occ == 3 && atoi(e_) == 2) occ = 2; }  // profiling switch
+  p.occ = occ;
   const int cap = sms * occ;
   grid = p.n_tiles < cap ? p.n_tiles : cap;
   smem_out = smem; cpr_out = cpr; is3_out = is3;
@@ -692,14 +817,24 @@ int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s) {
   const int tpe_ = tc2_tiles_per_event(d);
   p.fd_tpe = tc2::make_fastdiv(tpe_ > 0 ? tpe_ : 1);
   int rc = -2;
-#define IEA_TC2_LAUNCH(C_, I_, L_) if (cpr == C_ && is3 == I_ && leanb == L_) rc = launch(tc2::conv_tc2_kernel<C_, I_, L_>);
-  IEA_TC2_LAUNCH(2, true, 0) IEA_TC2_LAUNCH(2, true, 1) IEA_TC2_LAUNCH(2, true, 2)
-  IEA_TC2_LAUNCH(4, true, 0) IEA_TC2_LAUNCH(4, true, 1) IEA_TC2_LAUNCH(4, true, 2)
-  IEA_TC2_LAUNCH(8, true, 0) IEA_TC2_LAUNCH(8, true, 1) IEA_TC2_LAUNCH(8, true, 2)
-  IEA_TC2_LAUNCH(2, false, 0) IEA_TC2_LAUNCH(2, false, 1) IEA_TC2_LAUNCH(2, false, 2)
-  IEA_TC2_LAUNCH(4, false, 0) IEA_TC2_LAUNCH(4, false, 1) IEA_TC2_LAUNCH(4, false, 2)
-  IEA_TC2_LAUNCH(8, false, 0) IEA_TC2_LAUNCH(8, false, 1) IEA_TC2_LAUNCH(8, false, 2)
+  const int ko = cpr == 2 ? (p.occ == 3 ? 3 : 2) : (cpr == 4 ? 2 : 1);  // launch-bound variant of the kernel
+#define IEA_TC2_LAUNCH(C_, I_, L_, O_) \
+  if (cpr == C_ && is3 == I_ && leanb == L_ && ko == O_) rc = launch(tc2::conv_tc2_kernel<C_, I_, L_, O_>);
+  IEA_TC2_LAUNCH(2, true, 0, 3) IEA_TC2_LAUNCH(2, true, 1, 3) IEA_TC2_LAUNCH(2, true, 2, 3)
+  IEA_TC2_LAUNCH(2, true, 0, 2) IEA_TC2_LAUNCH(2, true, 1, 2) IEA_TC2_LAUNCH(2, true, 2, 2)
+  IEA_TC2_LAUNCH(4, true, 0, 2) IEA_TC2_LAUNCH(4, true, 1, 2) IEA_TC2_LAUNCH(4, true, 2, 2)
+  IEA_TC2_LAUNCH(8, true, 0, 1) IEA_TC2_LAUNCH(8, true, 1, 1) IEA_TC2_LAUNCH(8, true, 2, 1)
+  IEA_TC2_LAUNCH(2, false, 0, 3) IEA_TC2_LAUNCH(2, false, 1, 3) IEA_TC2_LAUNCH(2, false, 2, 3)
+  IEA_TC2_LAUNCH(2, false, 0, 2) IEA_TC2_LAUNCH(2, false, 1, 2) IEA_TC2_LAUNCH(2, false, 2, 2)
+  IEA_TC2_LAUNCH(4, false, 0, 2) IEA_TC2_LAUNCH(4, false, 1, 2) IEA_TC2_LAUNCH(4, false, 2, 2)
+  IEA_TC2_LAUNCH(8, false, 0, 1) IEA_TC2_LAUNCH(8, false, 1, 1) IEA_TC2_LAUNCH(8, false, 2, 1)
 #undef IEA_TC2_LAUNCH
   if (rc) return rc;
   return check_launch("iea_conv_fprop(tcgen05 resident)");
 }
+
+#ifdef IEA_TC2_TRACE
+extern "C" int iea_debug_tc2_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, tc2::g_trace, sizeof(long long) * 8 * 512);
+}
+#endif
