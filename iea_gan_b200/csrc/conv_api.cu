@@ -9,12 +9,16 @@ int iea_conv_fprop_tc(const iea_conv_desc* d, cudaStream_t s);
 int iea_conv_tc_ok(const iea_conv_desc* d);
 int iea_conv_tc2_ok(const iea_conv_desc* d);
 int iea_conv_fprop_tc2(const iea_conv_desc* d, cudaStream_t s);
+int iea_conv_thin_ok(const iea_conv_desc* d);
+int iea_conv_fprop_thin(const iea_conv_desc* d, cudaStream_t s);
+int iea_conv_thin_stats_slots(const iea_conv_desc* d);
 
 // tcgen05 variant selection: resident-weights/patch kernel when it applies, else the streaming one.
 // IEA_TC_VARIANT=stream forces the streaming kernel (used by the tests to cover both).
 static int run_tc(const iea_conv_desc* d, cudaStream_t s) {
   const char* v = getenv("IEA_TC_VARIANT");
   const bool force_stream = v && v[0] == 's';
+  if (!force_stream && iea_conv_thin_ok(d)) return iea_conv_fprop_thin(d, s);
   if ((!force_stream || !iea_conv_tc_ok(d)) && iea_conv_tc2_ok(d)) return iea_conv_fprop_tc2(d, s);
   return iea_conv_fprop_tc(d, s);
 }
@@ -39,6 +43,8 @@ extern "C" int iea_conv_stats_slots(const iea_conv_desc* d) {
   if (d->impl == IEA_IMPL_GENERIC) return tiles;
   const char* v = getenv("IEA_TC_VARIANT");
   const bool force_stream = v && v[0] == 's';
+  if (!iea_conv_tc_ok(d) && !iea_conv_tc2_ok(d)) return tiles;  // generic kernel
+  if (!force_stream && iea_conv_thin_ok(d)) return iea_conv_thin_stats_slots(d);
   if ((!force_stream || !iea_conv_tc_ok(d)) && iea_conv_tc2_ok(d)) return iea_conv_tc2_stats_slots(d);
   return tiles;
 }

@@ -1,0 +1,591 @@
+// conv_thin.cu -- tcgen05 / TMEM convolution for the thin, high-resolution IEA-GAN layers
+// (Cin 16..64, Cout 16/32; 3x3 and 1x1), the layers that carry most of the HBM traffic of G and D
+// (16->16 / 32->32 3x3 at 128^2..256^2, 64->16 / 16->32 1x1, layers.py:169-206).
+//
+// These layers move 64..192 bytes per output pixel, so at the HBM rate an SM has only a few hundred
+// issue slots per 128-pixel UMMA tile.  conv_tc2.cu spends ~2000; this kernel is built to spend ~400:
+//   * MACRO TILES: one pipeline item is MT side-by-side 16x8 tiles (3x3: one 18 x (8*MT+2) halo patch,
+//     1x1: MT*128 consecutive pixels).  Barrier hand-offs, tile bookkeeping and halo re-reads are paid
+//     once per macro tile; the MT accumulators live side by side in TMEM.
+//   * every producer thread owns the same chunk slots of every patch, so the global / shared offsets of
+//     its 16-byte cp.async copies are computed once per kernel (nearest-up2 folded into the offsets);
+//     a macro tile costs one 64-bit add + one cp.async per chunk, and one LDS / 4 HFMA2 / STS for the
+//     fused BN-affine + ReLU prologue in place.  Border patches use per-slot side masks (no coordinates).
+//   * the MMA issuer is warp-uniform code around elect.sync, so descriptors stay in uniform registers;
+//   * the epilogue keeps one pixel per thread: packed fp32x2 math (FFMA2 / FADD2), 16-byte stores to
+//     its own NHWC row, batch-norm partial sums in registers across the whole run of tiles.
+// Shapes outside this envelope (pooled inputs, Cout > 32, Cin > 64, the 1-channel stem) stay on
+// conv_tc2.cu / conv_tc.cu.
+#include "tc_common.cuh"
+#include <stdlib.h>
+using namespace iea;
+
+namespace thin {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int THREADS = 288;  // warp 0: MMA issuer, warps 1-4: producers, warps 5-8: epilogue
+
+struct FastDiv { uint32_t mul, shr, d; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d;
+  if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  f.shr = s;
+  f.mul = (uint32_t)(((1ull << (32 + s)) + d - 1) / d - (1ull << 32));
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  const uint32_t t = __umulhi(n, f.mul);
+  return (t + ((n - t) >> 1)) >> (f.shr - 1);
+}
+
+// compile-time geometry shared by the kernel and the launcher
+template <int CPR, bool IS3, int MT>
+struct Geo {
+  static constexpr int PW = 8 * MT + 2;                       // patch pitch in pixels (3x3)
+  static constexpr int NPIX = IS3 ? 18 * PW : BM * MT;        // staged pixels per macro tile
+  static constexpr int NCH = NPIX * CPR;                      // 16-byte chunks per macro tile
+  static constexpr int NS = (NCH + 127) / 128;                // chunk slots per producer thread
+  // planes (8 channels each) are skewed by 128/CPR bytes so that the CPR chunks of a pixel, written by
+  // consecutive threads, fall into different shared-memory banks
+  static constexpr uint32_t PLANE = (NPIX * 16 + 127) / 128 * 128 + 128 / CPR;
+  static constexpr uint32_t STAGE = (CPR * PLANE + 127) / 128 * 128;
+};
+
+struct Params {
+  iea_conv_desc d;
+  const bf16* wtc;
+  FastDiv fd_mtw, fd_mth, fd_tpe, fd_w, fd_h;
+  int M;                  // output pixels (< 2^31)
+  int n_macro;            // macro tiles
+  int mtw, mth;           // macro tiles per image row / per image column (1x1: per image / 1)
+  int hs, ws;             // stored input resolution
+  int stages, depth;
+  uint32_t w_bytes, stage_off, misc_off, bar_off, tmem_cols;
+};
+
+struct Pos { int n, th, tw; };
+__device__ __forceinline__ Pos pos_of(const Params& p, int g) {
+  Pos c;
+  const unsigned t = fdiv((unsigned)g, p.fd_mtw);
+  c.tw = (int)((unsigned)g - t * (unsigned)p.mtw);
+  c.n = (int)fdiv(t, p.fd_mth);
+  c.th = (int)(t - (unsigned)c.n * (unsigned)p.mth);
+  return c;
+}
+__device__ __forceinline__ void pos_next(const Params& p, Pos& c) {
+  if (++c.tw == p.mtw) { c.tw = 0; if (++c.th == p.mth) { c.th = 0; ++c.n; } }
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return r;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return r;
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int CPR, bool IS3, int NB, int MT>
+__global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params p) {
+  using G = Geo<CPR, IS3, MT>;
+  constexpr int PW = G::PW, NCH = G::NCH, NS = G::NS;
+  constexpr uint32_t PLANE = G::PLANE, STAGE = G::STAGE;
+  constexpr int TAPS = IS3 ? 9 : 1;
+  constexpr int BN = 16 * NB;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const iea_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + p.bar_off;
+  const int S = p.stages;
+  // barriers: full[S] | empty[S] | tfull[2] | tempty[2] | w
+  const uint32_t full0 = bar0, empty0 = bar0 + 8u * S, tfull0 = bar0 + 16u * S, tempty0 = tfull0 + 16, w_bar = tfull0 + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.bar_off + 16 * S + 40);
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // blocked partition: each CTA owns a contiguous run of macro tiles
+  const int g_base = p.n_macro / (int)gridDim.x, g_rem = p.n_macro % (int)gridDim.x;
+  const int my_n = g_base + ((int)blockIdx.x < g_rem ? 1 : 0);
+  const int g0 = (int)blockIdx.x * g_base + ((int)blockIdx.x < g_rem ? (int)blockIdx.x : g_rem);
+
+  if (warp == 0) {
+    // ===================== weight TMA + MMA issuer (warp-uniform; one elected lane issues) =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, p.w_bytes);
+      for (uint32_t off = 0; off < p.w_bytes; off += 32768) {
+        const uint32_t nb = p.w_bytes - off < 32768 ? p.w_bytes - off : 32768;
+        bulk_g2s(sbase + off, (const uint8_t*)p.wtc + off, nb, w_bar);
+      }
+    }
+    mbar_wait(w_bar, 0);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t LBO_B = BN * 16;
+    const uint64_t da_base = make_desc(sbase + p.stage_off, PLANE, IS3 ? PW * 16 : 128);
+    const uint64_t db_base = make_desc(sbase, LBO_B, 128);
+    uint32_t s = 0, ph = 0;
+    for (int t = 0; t < my_n; ++t) {
+      const uint32_t ab = t & 1, aph = (t >> 1) & 1;
+      mbar_wait(tempty0 + 8 * ab, aph ^ 1);
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a16 = s * (STAGE >> 4);
+        const uint32_t tacc = tmem_base + ab * (MT * BN);
+#pragma unroll
+        for (int sb = 0; sb < MT; ++sb) {
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
+#pragma unroll
+            for (int j = 0; j < CPR / 2; ++j) {
+              const uint32_t a_off = a16 + (IS3 ? sb * 8 + (tap / 3) * PW + (tap % 3) : sb * BM) + 2 * j * (PLANE >> 4);
+              const uint32_t b_off = (uint32_t)((tap * CPR + 2 * j) * (LBO_B >> 4));
+              tc_mma(tacc + sb * BN, da_base + a_off, db_base + b_off, idesc, (tap > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+        }
+        tc_commit(empty0 + 8 * s);
+        tc_commit(tfull0 + 8 * ab);
+      }
+      __syncwarp();
+      if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+    }
+  } else if (warp <= 4) {
+    // ===================== patch producers =====================
+    const int pt = tid - 32;
+    const int cc = pt % CPR;                                   // this thread's 8-channel plane (fixed: 128 % CPR == 0)
+    const bool affine = d.in_scale != nullptr;
+    const bool relu = d.in_relu != 0;
+    const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
+    const int D = p.depth;
+    // slot table: chunk q = pt + 128*i of the macro patch -> (global element offset, smem byte offset) and,
+    // for 3x3, which patch sides it lies on (bit i of top/bot/left/right).  Tile independent.
+    int goff[NS];
+    uint32_t soff[NS];
+    uint32_t m_top = 0, m_bot = 0, m_left = 0, m_right = 0, m_valid = 0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const int q = pt + 128 * i;
+      const int pp = q / CPR;  // patch pixel
+      if (q < NCH) m_valid |= 1u << i;
+      if (IS3) {
+        const int pi = pp / PW, pj = pp - pi * PW;
+        goff[i] = (((pi - 1) >> sh_) * p.ws + ((pj - 1) >> sh_)) * d.x_ld + cc * 8;
+        if (pi == 0) m_top |= 1u << i;
+        if (pi == 17) m_bot |= 1u << i;
+        if (pj == 0) m_left |= 1u << i;
+        if (pj == PW - 1) m_right |= 1u << i;
+      } else {
+        goff[i] = pp * d.x_ld + cc * 8;
+      }
+      soff[i] = cc * PLANE + pp * 16;
+    }
+    const bf16* xb = (const bf16*)d.x;
+    const uint32_t st0 = sbase + p.stage_off;
+
+    struct Cur { uint32_t s, ph; int t; Pos c; };
+    auto cur_next = [&](Cur& c) {
+      if (++c.s == (uint32_t)S) { c.s = 0; c.ph ^= 1; }
+      ++c.t;
+      pos_next(p, c.c);
+    };
+    // slots of this macro tile that are conv padding (3x3) or beyond the last pixel (1x1 tail)
+    auto pad_mask = [&](const Cur& c) -> uint32_t {
+      if (IS3) {
+        return (c.c.th == 0 ? m_top : 0u) | (c.c.th == p.mth - 1 ? m_bot : 0u) | (c.c.tw == 0 ? m_left : 0u) |
+               (c.c.tw == p.mtw - 1 ? m_right : 0u);
+      }
+      const int left = p.M - (g0 + c.t) * (BM * MT);  // pixels left from the macro tile's first one
+      if (left >= BM * MT) return 0u;
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+        if ((pt + 128 * i) / CPR >= left) m |= 1u << i;
+      return m;
+    };
+    auto issue = [&](const Cur& c) {
+      mbar_wait(empty0 + 8 * c.s, c.ph ^ 1);
+      int64_t base;
+      if (IS3) base = ((int64_t)(c.c.n * p.hs + ((c.c.th * 16) >> sh_)) * p.ws + ((c.c.tw * (8 * MT)) >> sh_)) * d.x_ld;
+      else base = (int64_t)(g0 + c.t) * (BM * MT) * d.x_ld;
+      const bf16* bp = xb + base;
+      const uint32_t a = st0 + c.s * STAGE;
+      const uint32_t pad = pad_mask(c);
+      if (pad == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+          if (i < NS - 1 || (m_valid >> i & 1))
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a + soff[i]), "l"(bp + goff[i]) : "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          if (!(m_valid >> i & 1)) continue;
+          if (pad >> i & 1) asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a + soff[i]), "r"(0) : "memory");
+          else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a + soff[i]), "l"(bp + goff[i]) : "memory");
+        }
+      }
+    };
+
+    Cur ci, ct;
+    ci.s = 0; ci.ph = 0; ci.t = 0; ci.c = pos_of(p, g0);
+    ct = ci;
+    for (int k = 0; k < D - 1; ++k) {
+      if (ci.t < my_n) { issue(ci); cur_next(ci); }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __nv_bfloat162 sc2[4], sh2[4];
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+    int ss_n = -1;
+    for (int it = 0; it < my_n; ++it) {
+      if (ci.t < my_n) { issue(ci); cur_next(ci); }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else asm volatile("cp.async.wait_group 3;" ::: "memory");
+      if (affine || relu) {  // fused prologue, in place on the chunks this thread copied
+        if (affine && ct.c.n != ss_n) {
+          ss_n = ct.c.n;
+          const int64_t si = (d.in_bcast ? 0 : (int64_t)ss_n * d.cin) + cc * 8;
+          const float4 a0 = *reinterpret_cast<const float4*>(d.in_scale + si), a1 = *reinterpret_cast<const float4*>(d.in_scale + si + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(d.in_shift + si), b1 = *reinterpret_cast<const float4*>(d.in_shift + si + 4);
+          sc2[0] = __floats2bfloat162_rn(a0.x, a0.y); sc2[1] = __floats2bfloat162_rn(a0.z, a0.w);
+          sc2[2] = __floats2bfloat162_rn(a1.x, a1.y); sc2[3] = __floats2bfloat162_rn(a1.z, a1.w);
+          sh2[0] = __floats2bfloat162_rn(b0.x, b0.y); sh2[1] = __floats2bfloat162_rn(b0.z, b0.w);
+          sh2[2] = __floats2bfloat162_rn(b1.x, b1.y); sh2[3] = __floats2bfloat162_rn(b1.z, b1.w);
+        }
+        const uint32_t live = m_valid & ~pad_mask(ct);  // padding stays zero: relu(shift) != 0
+        uint8_t* a = smem + p.stage_off + ct.s * STAGE;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          if (!(live >> i & 1)) continue;
+          uint4* q = reinterpret_cast<uint4*>(a + soff[i]);
+          uint4 v = *q;
+          __nv_bfloat162* x2 = reinterpret_cast<__nv_bfloat162*>(&v);
+          if (affine && relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x2[j] = __hfma2_relu(x2[j], sc2[j], sh2[j]);
+          } else if (affine) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x2[j] = __hfma2(x2[j], sc2[j], sh2[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x2[j] = __hmax2(x2[j], zero2);
+          }
+          *q = v;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(full0 + 8 * ct.s);
+      cur_next(ct);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    // ===================== epilogue: one output pixel per thread =====================
+    const int q = warp & 3, et = q * 32 + lane;  // TMEM lane == tile row
+    float* ep_sc = reinterpret_cast<float*>(smem + p.misc_off);
+    float* ep_bs = ep_sc + BN;
+    float* fold = ep_bs + BN;  // [4 warps][2*BN]
+    for (int c = et; c < BN; c += 128) {
+      ep_sc[c] = d.out_scale ? d.out_scale[d.out_scale_stride ? c : 0] : 1.f;
+      ep_bs[c] = d.bias ? d.bias[c] : 0.f;
+    }
+    bar_sync_epi();
+    const bool has_sb = d.out_scale != nullptr || d.bias != nullptr;
+    const bool has_stats = d.stats != nullptr;
+    const bool has_res = d.res != nullptr;
+    const bool need_px = IS3 || (has_res && d.res_mode != IEA_IN_DIRECT);
+    // (sums are taken on the fp32 values before the bf16 rounding of the store: the rounding error is
+    // zero-mean and 2^-9 relative, far below the noise of the batch statistics themselves)
+    float2 s1[BN / 2], s2[BN / 2];
+#pragma unroll
+    for (int j = 0; j < BN / 2; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = s1[j]; }
+    auto flush = [&](int ev) {
+#pragma unroll
+      for (int j = 0; j < BN / 2; ++j) {
+        s1[j].x = warp_sum(s1[j].x); s1[j].y = warp_sum(s1[j].y);
+        s2[j].x = warp_sum(s2[j].x); s2[j].y = warp_sum(s2[j].y);
+      }
+      if (lane == 0)
+#pragma unroll
+        for (int j = 0; j < BN / 2; ++j) {
+          fold[(q * BN + 2 * j) * 2] = s1[j].x; fold[(q * BN + 2 * j) * 2 + 1] = s2[j].x;
+          fold[(q * BN + 2 * j + 1) * 2] = s1[j].y; fold[(q * BN + 2 * j + 1) * 2 + 1] = s2[j].y;
+        }
+      bar_sync_epi();
+      for (int c = et; c < BN * 2; c += 128) {
+        const float a = fold[c] + fold[BN * 2 + c] + fold[2 * BN * 2 + c] + fold[3 * BN * 2 + c];
+        d.stats[((int64_t)ev * gridDim.x + blockIdx.x) * BN * 2 + c] = a;
+      }
+      bar_sync_epi();
+#pragma unroll
+      for (int j = 0; j < BN / 2; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = s1[j]; }
+    };
+    const int tpe = (int)p.fd_tpe.d;  // macro tiles per event (batch statistics are per event)
+    int ev = (int)fdiv((unsigned)g0, p.fd_tpe), ev_pos = g0 - ev * tpe;
+    Pos c = pos_of(p, g0);
+    const int er = et >> 3, ec = et & 7;
+    bf16* const yb = (bf16*)d.y;
+    const bf16* const rp = (const bf16*)d.res;
+    for (int t = 0; t < my_n; ++t) {
+      const uint32_t ab = t & 1, aph = (t >> 1) & 1;
+      int m0, oh = 0, ow0 = 0;
+      const int nn = c.n;
+      if (IS3) {
+        oh = c.th * 16 + er; ow0 = c.tw * (8 * MT) + ec;
+        m0 = (nn * d.h + oh) * d.w + ow0;
+      } else {
+        m0 = (g0 + t) * (BM * MT) + et;
+      }
+      pos_next(p, c);
+      if (has_stats) {
+        if (ev_pos == tpe) { flush(ev); ++ev; ev_pos = 0; }
+        ++ev_pos;
+      }
+      mbar_wait(tfull0 + 8 * ab, aph);
+      tc_fence_after();
+#pragma unroll
+      for (int sb = 0; sb < MT; ++sb) {
+        const int m = m0 + (IS3 ? sb * 8 : sb * BM);
+        const bool valid = IS3 || m < p.M;
+        int rn = nn, roh = oh, row = ow0 + sb * 8;
+        if (!IS3 && need_px && valid) {
+          const unsigned t1 = fdiv((unsigned)m, p.fd_w);
+          row = (int)((unsigned)m - t1 * (unsigned)d.w); rn = (int)fdiv(t1, p.fd_h); roh = (int)(t1 - (unsigned)rn * (unsigned)d.h);
+        }
+#pragma unroll
+        for (int cb = 0; cb < NB; ++cb) {
+          uint32_t raw[16];
+          tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + ab * (MT * BN) + sb * BN + cb * 16, raw);
+          tmem_ld_wait();
+          if (valid) {  // (no early `continue`: all lanes must reconverge before the next aligned tcgen05.ld)
+            const int c0 = cb * 16;
+            float2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+            if (has_sb) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
+                const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
+                v[2 * j4] = ffma2(v[2 * j4], make_float2(s4.x, s4.y), make_float2(b4.x, b4.y));
+                v[2 * j4 + 1] = ffma2(v[2 * j4 + 1], make_float2(s4.z, s4.w), make_float2(b4.z, b4.w));
+              }
+            }
+            if (has_res && c0 < d.res_c) {
+              if (d.res_mode == IEA_IN_POOL2) {
+                const float2 quarter = make_float2(0.25f, 0.25f);
+                for (int a = 0; a < 2; ++a)
+                  for (int b = 0; b < 2; ++b) {
+                    const bf16* sp = rp + (((int64_t)rn * (2 * d.h) + 2 * roh + a) * (2 * d.w) + 2 * row + b) * d.res_ld + c0;
+                    const uint4 r0 = *reinterpret_cast<const uint4*>(sp), r1 = *reinterpret_cast<const uint4*>(sp + 8);
+                    const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = ffma2(bf2_to_f2(w[j]), quarter, v[j]);
+                  }
+              } else {
+                const bf16* sp = d.res_mode == IEA_IN_UP2
+                                     ? rp + (((int64_t)rn * (d.h >> 1) + (roh >> 1)) * (d.w >> 1) + (row >> 1)) * d.res_ld + c0
+                                     : rp + (int64_t)m * d.res_ld + c0;
+                const uint4 r0 = *reinterpret_cast<const uint4*>(sp), r1 = *reinterpret_cast<const uint4*>(sp + 8);
+                const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
+              }
+            }
+            uint4* yp = reinterpret_cast<uint4*>(yb + (int64_t)m * d.y_ld + c0);
+            if (d.acc_c0 >= 0 && c0 >= d.acc_c0) {
+              const uint4 r0 = yp[0], r1 = yp[1];
+              const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
+            }
+            if (d.act == IEA_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); }
+            } else if (d.act == IEA_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j].x = tanhf(v[j].x); v[j].y = tanhf(v[j].y); }
+            }
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = pack2(v[j].x, v[j].y);
+            yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            if (has_stats) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { s1[cb * 8 + j] = fadd2(s1[cb * 8 + j], v[j]); s2[cb * 8 + j] = ffma2(v[j], v[j], s2[cb * 8 + j]); }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * ab);
+    }
+    if (has_stats && my_n > 0) flush(ev);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+}  // namespace thin
+
+int iea_conv_tc_base_ok(const iea_conv_desc* d, int padded);
+
+// macro-tile width (in 16x8 / 128-pixel tiles) the kernel uses for this layer; 0: layer not eligible
+static int thin_mt(const iea_conv_desc* d) {
+  if (!iea_conv_tc_base_ok(d, 0)) return 0;
+  { const char* e_ = getenv("IEA_THIN"); if (e_ && e_[0] == '0') return 0; }  // profiling switch: old kernels only
+  if (d->cout != 16 && d->cout != 32) return 0;
+  if (d->cin != 16 && d->cin != 32 && d->cin != 64) return 0;
+  if (d->y_dtype != IEA_BF16 || d->cin < 16) return 0;
+  if (d->in_mode == IEA_IN_POOL2) return 0;
+  const int64_t M = d->n * (int64_t)d->h * d->w;
+  if (M >= (1ll << 31) || M * (int64_t)(d->x_ld > d->y_ld ? d->x_ld : d->y_ld) >= (1ll << 40)) return 0;
+  const int want = d->cin == 16 ? 4 : (d->cin == 32 ? 2 : 1);
+  if (d->ksize == 3) {
+    if (d->h % 16 || d->w % 8) return 0;
+    int mt = want;
+    while (mt > 1 && d->w % (8 * mt)) mt >>= 1;
+    return mt;
+  }
+  if (d->in_mode != IEA_IN_DIRECT) return 0;
+  int mt = want;
+  const int64_t hw = (int64_t)d->h * d->w;
+  // images must be whole macro tiles when a per-image prologue or per-event statistics are fused
+  while (mt > 1 && hw % (128 * mt)) mt >>= 1;
+  if ((d->in_scale || d->stats) && hw % (128 * mt)) return 0;
+  return mt;
+}
+int iea_conv_thin_ok(const iea_conv_desc* d) {
+  if (!thin_mt(d)) return 0;
+  if (d->stats && (d->n % 40)) return 0;
+  return 1;
+}
+
+template <int CPR, bool IS3, int MT>
+static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint32_t& smem) {
+  using G = thin::Geo<CPR, IS3, MT>;
+  p.d = *d;
+  p.wtc = (const bf16*)d->wpack_tc;
+  p.M = (int)(d->n * (int64_t)d->h * d->w);
+  p.hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : d->h;
+  p.ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : d->w;
+  const int hw = d->h * d->w;
+  if (IS3) {
+    p.mtw = d->w / (8 * MT); p.mth = d->h / 16;
+    p.n_macro = (int)(d->n * (int64_t)p.mtw * p.mth);
+  } else {
+    p.n_macro = (p.M + 128 * MT - 1) / (128 * MT);
+    p.mtw = hw % (128 * MT) == 0 ? hw / (128 * MT) : p.n_macro + 1;  // (never wraps when images are not whole tiles)
+    p.mth = 1;
+  }
+  p.fd_mtw = thin::make_fastdiv(p.mtw); p.fd_mth = thin::make_fastdiv(p.mth);
+  p.fd_w = thin::make_fastdiv(d->w); p.fd_h = thin::make_fastdiv(d->h);
+  const int64_t per_event = IS3 ? 40ll * p.mtw * p.mth : (40ll * hw) / (128 * MT);
+  p.fd_tpe = thin::make_fastdiv(per_event > 0 ? (uint32_t)per_event : 1u);
+  const int taps = IS3 ? 9 : 1;
+  p.w_bytes = (uint32_t)(d->cout * d->cin * taps * 2);
+  p.stage_off = (p.w_bytes + 127) / 128 * 128;
+  const uint32_t misc = (2 * d->cout + 4 * 2 * d->cout) * 4;  // scale, bias, statistics fold
+  const uint32_t tail = misc + 256;
+  int stages = 4;
+  while (stages > 2 && p.stage_off + stages * G::STAGE + tail > 110 * 1024) --stages;
+  p.stages = stages;
+  p.depth = stages >= 4 ? 3 : 2;
+  if (stages == 2) p.depth = 2;
+  p.misc_off = p.stage_off + stages * G::STAGE;
+  p.bar_off = (p.misc_off + misc + 15) / 16 * 16;
+  smem = p.bar_off + 256;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * MT * d->cout)) cols <<= 1;
+  p.tmem_cols = cols;
+  IEA_CHECK_ARG(smem <= 220 * 1024 && cols <= 512, "iea_conv_fprop(tcgen05 thin): tile does not fit (cin=%d cout=%d k=%d)",
+                d->cin, d->cout, d->ksize);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int occ = (smem <= 110 * 1024 && cols <= 256) ? 2 : 1;
+  const int cap = sms * occ;
+  grid = p.n_macro < cap ? p.n_macro : cap;
+  return 0;
+}
+
+template <int CPR, bool IS3, int NB, int MT>
+static int thin_launch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
+  thin::Params p; int grid = 0; uint32_t smem = 0;
+  int rc = thin_prepare<CPR, IS3, MT>(d, p, grid, smem);
+  if (rc) return rc;
+  if (grid_only) { *grid_only = grid; return 0; }
+  auto kern = thin::conv_thin_kernel<CPR, IS3, NB, MT>;
+  IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, thin::THREADS, smem, s>>>(p);
+  return check_launch("iea_conv_fprop(tcgen05 thin)");
+}
+
+static int thin_dispatch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
+  const int mt = thin_mt(d), cpr = d->cin / 8, nb = d->cout / 16;
+  const bool is3 = d->ksize == 3;
+#define IEA_THIN_CASE(C_, I_, N_, M_) \
+  if (cpr == C_ && is3 == I_ && nb == N_ && mt == M_) return thin_launch<C_, I_, N_, M_>(d, s, grid_only);
+#define IEA_THIN_MTS(C_, I_, N_) IEA_THIN_CASE(C_, I_, N_, 1) IEA_THIN_CASE(C_, I_, N_, 2)
+  IEA_THIN_MTS(2, true, 1) IEA_THIN_MTS(2, true, 2) IEA_THIN_CASE(2, true, 1, 4) IEA_THIN_CASE(2, true, 2, 4)
+  IEA_THIN_MTS(4, true, 1) IEA_THIN_MTS(4, true, 2)
+  IEA_THIN_CASE(8, true, 1, 1) IEA_THIN_CASE(8, true, 2, 1)
+  IEA_THIN_MTS(2, false, 1) IEA_THIN_MTS(2, false, 2) IEA_THIN_CASE(2, false, 1, 4) IEA_THIN_CASE(2, false, 2, 4)
+  IEA_THIN_MTS(4, false, 1) IEA_THIN_MTS(4, false, 2)
+  IEA_THIN_CASE(8, false, 1, 1) IEA_THIN_CASE(8, false, 2, 1)
+#undef IEA_THIN_MTS
+#undef IEA_THIN_CASE
+  set_error("iea_conv_fprop(tcgen05 thin): no kernel for cin=%d cout=%d k=%d mt=%d", d->cin, d->cout, d->ksize, mt);
+  return -2;
+}
+
+int iea_conv_fprop_thin(const iea_conv_desc* d, cudaStream_t s) { return thin_dispatch(d, s, nullptr); }
+// statistics slots per event = CTAs of the launch (each CTA folds its run of tiles per event)
+int iea_conv_thin_stats_slots(const iea_conv_desc* d) {
+  int grid = 0;
+  if (thin_dispatch(d, nullptr, &grid)) return 0;
+  return grid;
+}

@@ -238,6 +238,25 @@ def test_layernorm_mha_l2norm(eng):
     (128, 32, 1, 0, True, True, None, (16, 16)), (16, 64, 1, 0, True, True, 1, (16, 16))])
 @pytest.mark.parametrize("variant", ["resident", "stream"])
 def test_conv_tcgen05_matches_generic(eng, variant, cin, cout, k, mode, relu, aff, resm, hw):
+    _tc_vs_generic(eng, variant, cin, cout, k, mode, relu, aff, resm, hw, 40)
+
+
+@pytest.mark.parametrize("cin,cout,k,mode,relu,aff,resm,hw,n", [
+    (16, 16, 3, 0, True, True, None, (32, 64), 80),   # 4-wide macro tiles, interior + border patches, 2 events
+    (16, 16, 3, 1, True, True, 1, (32, 32), 80),      # nearest-up2 input folded into the chunk offsets
+    (16, 32, 1, 0, True, True, 1, (32, 32), 80),      # 1x1, up2 residual (GBlock conv4 + shortcut)
+    (16, 32, 1, 0, False, False, 2, (16, 16), 40),    # pooled residual
+    (32, 16, 3, 0, True, False, None, (16, 32), 40),  # 2-wide macro tiles
+    (32, 32, 3, 0, True, True, 0, (32, 16), 80),
+    (64, 32, 3, 0, True, True, None, (16, 16), 40),   # single-tile patches, 8 planes
+    (64, 16, 1, 0, True, True, None, (16, 24), 40),   # 1x1 whose images are 3 tiles (macro width falls to 1)
+    (32, 32, 1, 0, False, False, None, (12, 20), 40)])  # ragged tail: 9600 pixels = 37.5 macro tiles
+def test_conv_thin_macro_tiles(eng, cin, cout, k, mode, relu, aff, resm, hw, n):
+    """conv_thin.cu (macro-tile tcgen05 kernel for Cin <= 64, Cout 16/32) against the CUDA-core kernel."""
+    _tc_vs_generic(eng, "resident", cin, cout, k, mode, relu, aff, resm, hw, n)
+
+
+def _tc_vs_generic(eng, variant, cin, cout, k, mode, relu, aff, resm, hw, n):
     """The tcgen05/TMEM implicit-GEMM path against the CUDA-core path on the same descriptor: same
     bf16 inputs and weights, fp32 accumulation in both, so they agree to bf16 output rounding
     (<= 1 ulp of bf16 = 2^-8 relative per element; 6e-3 relative L2 bound) -- forward, statistics
@@ -248,7 +267,6 @@ def test_conv_tcgen05_matches_generic(eng, variant, cin, cout, k, mode, relu, af
         dev = "cuda"
         torch.manual_seed(5)
         h, w = hw
-        n = 40
         hs, ws = (h // 2, w // 2) if mode == 1 else ((2 * h, 2 * w) if mode == 2 else (h, w))
         m = make_sn_conv(cin, cout, k, dev)
         m.train()
