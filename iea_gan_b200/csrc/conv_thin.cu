@@ -24,7 +24,9 @@ namespace thin {
 using namespace tc;
 
 constexpr int BM = 128;
-constexpr int THREADS = 288;  // warp 0: MMA issuer, warps 1-4: producers, warps 5-8: epilogue
+constexpr int THREADS = 512;  // warps 0-7: two producer groups (they also issue their tiles' MMAs), warps 8-15: two epilogue groups
+                              // (one CTA per SM; the groups take alternate macro tiles so every hand-off latency is
+                              // covered by the other group's tile)
 
 struct FastDiv { uint32_t mul, shr, d; };
 inline FastDiv make_fastdiv(uint32_t d) {
@@ -55,6 +57,14 @@ struct Geo {
   static constexpr uint32_t STAGE = (CPR * PLANE + 127) / 128 * 128;
 };
 
+#ifdef IEA_THIN_TRACE
+// pipeline trace of CTA 0 (profiling builds only): clock64 stamps per role and macro tile
+__device__ long long g_trace[8][512];
+#define TRACE(slot, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_trace[slot][idx] = clock64(); } while (0)
+#else
+#define TRACE(slot, idx) do { } while (0)
+#endif
+
 struct Params {
   iea_conv_desc d;
   const bf16* wtc;
@@ -63,7 +73,7 @@ struct Params {
   int n_macro;            // macro tiles
   int mtw, mth;           // macro tiles per image row / per image column (1x1: per image / 1)
   int hs, ws;             // stored input resolution
-  int stages, depth;
+  int stages, depth, dbg;
   uint32_t w_bytes, stage_off, misc_off, bar_off, tmem_cols;
 };
 
@@ -111,25 +121,27 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int CPR, bool IS3, int NB, int MT>
-__global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_constant__ Params p) {
   using G = Geo<CPR, IS3, MT>;
   constexpr int PW = G::PW, NCH = G::NCH, NS = G::NS;
   constexpr uint32_t PLANE = G::PLANE, STAGE = G::STAGE;
   constexpr int TAPS = IS3 ? 9 : 1;
   constexpr int BN = 16 * NB;
+  constexpr int NI = IS3 ? MT : 1;  // MMA-issuing warps per group: 3x3 -> producer warp w issues the 9*CPR/2 MMAs of sub-tile w
   extern __shared__ __align__(128) uint8_t smem[];
   const iea_conv_desc& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + p.bar_off;
-  const int S = p.stages;
-  // barriers: full[S] | empty[S] | tfull[2] | tempty[2] | w
-  const uint32_t full0 = bar0, empty0 = bar0 + 8u * S, tfull0 = bar0 + 16u * S, tempty0 = tfull0 + 16, w_bar = tfull0 + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.bar_off + 16 * S + 40);
+  const int S = p.stages;  // even: ring slot s belongs to group s & 1
+  // barriers: full[S] | empty[S] | tfull[4] | tempty[4] | w
+  const uint32_t full0 = bar0, empty0 = bar0 + 8u * S, tfull0 = bar0 + 16u * S, tempty0 = tfull0 + 32, w_bar = tfull0 + 64;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.bar_off + 16 * S + 72);
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
+    // one arrival per WARP on full / tempty (per-thread arrivals would wake every parked waiter 128 times)
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 4); mbar_init(empty0 + 8 * s, NI); }
+    for (int b = 0; b < 4; ++b) { mbar_init(tfull0 + 8 * b, NI); mbar_init(tempty0 + 8 * b, 4); }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -142,55 +154,16 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // blocked partition: each CTA owns a contiguous run of macro tiles
+  // blocked partition: each CTA owns a contiguous run of macro tiles; inside the CTA the two producer
+  // groups and the two epilogue groups take alternate macro tiles (group = item & 1)
   const int g_base = p.n_macro / (int)gridDim.x, g_rem = p.n_macro % (int)gridDim.x;
   const int my_n = g_base + ((int)blockIdx.x < g_rem ? 1 : 0);
   const int g0 = (int)blockIdx.x * g_base + ((int)blockIdx.x < g_rem ? (int)blockIdx.x : g_rem);
 
-  if (warp == 0) {
-    // ===================== weight TMA + MMA issuer (warp-uniform; one elected lane issues) =====================
-    if (lane == 0) {
-      mbar_expect_tx(w_bar, p.w_bytes);
-      for (uint32_t off = 0; off < p.w_bytes; off += 32768) {
-        const uint32_t nb = p.w_bytes - off < 32768 ? p.w_bytes - off : 32768;
-        bulk_g2s(sbase + off, (const uint8_t*)p.wtc + off, nb, w_bar);
-      }
-    }
-    mbar_wait(w_bar, 0);
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    constexpr uint32_t LBO_B = BN * 16;
-    const uint64_t da_base = make_desc(sbase + p.stage_off, PLANE, IS3 ? PW * 16 : 128);
-    const uint64_t db_base = make_desc(sbase, LBO_B, 128);
-    uint32_t s = 0, ph = 0;
-    for (int t = 0; t < my_n; ++t) {
-      const uint32_t ab = t & 1, aph = (t >> 1) & 1;
-      mbar_wait(tempty0 + 8 * ab, aph ^ 1);
-      mbar_wait(full0 + 8 * s, ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a16 = s * (STAGE >> 4);
-        const uint32_t tacc = tmem_base + ab * (MT * BN);
-#pragma unroll
-        for (int sb = 0; sb < MT; ++sb) {
-#pragma unroll
-          for (int tap = 0; tap < TAPS; ++tap) {
-#pragma unroll
-            for (int j = 0; j < CPR / 2; ++j) {
-              const uint32_t a_off = a16 + (IS3 ? sb * 8 + (tap / 3) * PW + (tap % 3) : sb * BM) + 2 * j * (PLANE >> 4);
-              const uint32_t b_off = (uint32_t)((tap * CPR + 2 * j) * (LBO_B >> 4));
-              tc_mma(tacc + sb * BN, da_base + a_off, db_base + b_off, idesc, (tap > 0 || j > 0) ? 1u : 0u);
-            }
-          }
-        }
-        tc_commit(empty0 + 8 * s);
-        tc_commit(tfull0 + 8 * ab);
-      }
-      __syncwarp();
-      if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
-    }
-  } else if (warp <= 4) {
-    // ===================== patch producers =====================
-    const int pt = tid - 32;
+  if (warp < 8) {
+    // ===================== patch producers: two groups of 4 warps, alternate macro tiles =====================
+    const int grp = warp >> 2, pw = warp & 3;
+    const int pt = tid & 127;
     const int cc = pt % CPR;                                   // this thread's 8-channel plane (fixed: 128 % CPR == 0)
     const bool affine = d.in_scale != nullptr;
     const bool relu = d.in_relu != 0;
@@ -222,9 +195,11 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
     const uint32_t st0 = sbase + p.stage_off;
 
     struct Cur { uint32_t s, ph; int t; Pos c; };
-    auto cur_next = [&](Cur& c) {
-      if (++c.s == (uint32_t)S) { c.s = 0; c.ph ^= 1; }
-      ++c.t;
+    auto cur_next = [&](Cur& c) {  // two macro tiles on: the other group owns the one in between
+      c.s += 2;
+      if (c.s >= (uint32_t)S) { c.s -= S; c.ph ^= 1; }
+      c.t += 2;
+      pos_next(p, c.c);
       pos_next(p, c.c);
     };
     // slots of this macro tile that are conv padding (3x3) or beyond the last pixel (1x1 tail)
@@ -243,6 +218,7 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
     };
     auto issue = [&](const Cur& c) {
       mbar_wait(empty0 + 8 * c.s, c.ph ^ 1);
+      if (p.dbg & 16) return;
       int64_t base;
       if (IS3) base = ((int64_t)(c.c.n * p.hs + ((c.c.th * 16) >> sh_)) * p.ws + ((c.c.tw * (8 * MT)) >> sh_)) * d.x_ld;
       else base = (int64_t)(g0 + c.t) * (BM * MT) * d.x_ld;
@@ -264,8 +240,49 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
       }
     };
 
+    // ---- MMA issue: warp pw < NI of the group issues sub-tile pw (3x3) / the whole item (1x1) of the group's
+    // items; warp-uniform code around elect.sync keeps the descriptors in uniform registers
+    if (tid == 0) {
+      mbar_expect_tx(w_bar, p.w_bytes);
+      for (uint32_t off = 0; off < p.w_bytes; off += 32768) {
+        const uint32_t nb = p.w_bytes - off < 32768 ? p.w_bytes - off : 32768;
+        bulk_g2s(sbase + off, (const uint8_t*)p.wtc + off, nb, w_bar);
+      }
+    }
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t LBO_B = BN * 16;
+    const uint64_t da_base = make_desc(sbase + p.stage_off, PLANE, IS3 ? PW * 16 : 128);
+    const uint64_t db_base = make_desc(sbase, LBO_B, 128);
+    auto mma_item = [&](int t, uint32_t s, uint32_t ph) {  // macro tile t of this CTA sits in ring slot s
+      const uint32_t ab = t & 3, aph = (t >> 2) & 1;
+      if (t < 2) mbar_wait(w_bar, 0);  // weights landed
+      mbar_wait(tempty0 + 8 * ab, aph ^ 1);
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      if (pt == 0) TRACE(3, t);
+      if (elect_one()) {
+        const uint32_t a16 = s * (STAGE >> 4);
+        const uint32_t tacc = tmem_base + ab * (MT * BN);
+        for (int sb = IS3 ? pw : 0; sb < MT; sb += NI) {
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
+#pragma unroll
+            for (int j = 0; j < CPR / 2; ++j) {
+              const uint32_t a_off = a16 + (IS3 ? sb * 8 + (tap / 3) * PW + (tap % 3) : sb * BM) + 2 * j * (PLANE >> 4);
+              const uint32_t b_off = (uint32_t)((tap * CPR + 2 * j) * (LBO_B >> 4));
+              if (!(p.dbg & 2)) tc_mma(tacc + sb * BN, da_base + a_off, db_base + b_off, idesc, (tap > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+        }
+        tc_commit(empty0 + 8 * s);
+        tc_commit(tfull0 + 8 * ab);
+      }
+      __syncwarp();
+      if (pt == 0) TRACE(4, t);
+    };
+
     Cur ci, ct;
-    ci.s = 0; ci.ph = 0; ci.t = 0; ci.c = pos_of(p, g0);
+    ci.s = grp; ci.ph = 0; ci.t = grp; ci.c = pos_of(p, g0 + grp);
     ct = ci;
     for (int k = 0; k < D - 1; ++k) {
       if (ci.t < my_n) { issue(ci); cur_next(ci); }
@@ -274,13 +291,14 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
     __nv_bfloat162 sc2[4], sh2[4];
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     int ss_n = -1;
-    for (int it = 0; it < my_n; ++it) {
+    for (; ct.t < my_n;) {
       if (ci.t < my_n) { issue(ci); cur_next(ci); }
       asm volatile("cp.async.commit_group;" ::: "memory");
       if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else asm volatile("cp.async.wait_group 3;" ::: "memory");
-      if (affine || relu) {  // fused prologue, in place on the chunks this thread copied
+      if (pt == 0) TRACE(0, ct.t);
+      if ((affine || relu) && !(p.dbg & 1)) {  // fused prologue, in place on the chunks this thread copied
         if (affine && ct.c.n != ss_n) {
           ss_n = ct.c.n;
           const int64_t si = (d.in_bcast ? 0 : (int64_t)ss_n * d.cin) + cc * 8;
@@ -293,45 +311,71 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
         }
         const uint32_t live = m_valid & ~pad_mask(ct);  // padding stays zero: relu(shift) != 0
         uint8_t* a = smem + p.stage_off + ct.s * STAGE;
+        // loads first, then the math, then the stores (predicated, no branches), at most 6 chunks at a time
+        constexpr int XB = 6;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) {
-          if (!(live >> i & 1)) continue;
-          uint4* q = reinterpret_cast<uint4*>(a + soff[i]);
-          uint4 v = *q;
-          __nv_bfloat162* x2 = reinterpret_cast<__nv_bfloat162*>(&v);
-          if (affine && relu) {
+        for (int i0 = 0; i0 < NS; i0 += XB) {
+          uint4 v[XB];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x2[j] = __hfma2_relu(x2[j], sc2[j], sh2[j]);
-          } else if (affine) {
+          for (int i = 0; i < XB; ++i)
+            if (i0 + i < NS && (live >> (i0 + i) & 1)) v[i] = *reinterpret_cast<const uint4*>(a + soff[i0 + i]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x2[j] = __hfma2(x2[j], sc2[j], sh2[j]);
-          } else {
+          for (int i = 0; i < XB; ++i) {
+            if (i0 + i >= NS) continue;
+            __nv_bfloat162* x2 = reinterpret_cast<__nv_bfloat162*>(&v[i]);
+            if (affine && relu) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x2[j] = __hmax2(x2[j], zero2);
+              for (int j = 0; j < 4; ++j) x2[j] = __hfma2_relu(x2[j], sc2[j], sh2[j]);
+            } else if (affine) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x2[j] = __hfma2(x2[j], sc2[j], sh2[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x2[j] = __hmax2(x2[j], zero2);
+            }
           }
-          *q = v;
+#pragma unroll
+          for (int i = 0; i < XB; ++i)
+            if (i0 + i < NS && (live >> (i0 + i) & 1)) *reinterpret_cast<uint4*>(a + soff[i0 + i]) = v[i];
         }
       }
+      if (pt == 0) TRACE(1, ct.t);
       fence_async_smem();
-      mbar_arrive(full0 + 8 * ct.s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + 8 * ct.s);
+      if (pt == 0) TRACE(2, ct.t);
+      if (pw < NI) mma_item(ct.t, ct.s, ct.ph);
       cur_next(ct);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
-    // ===================== epilogue: one output pixel per thread =====================
-    const int q = warp & 3, et = q * 32 + lane;  // TMEM lane == tile row
+    // ===================== epilogue: two groups of 4 warps, alternate macro tiles; one pixel per thread =====================
+    const int grp = (warp - 8) >> 2;
+    const int q = warp & 3, et = q * 32 + lane;  // TMEM lane == tile row (a warp may only touch lanes 32*(warp%4)..+31)
     float* ep_sc = reinterpret_cast<float*>(smem + p.misc_off);
     float* ep_bs = ep_sc + BN;
-    float* fold = ep_bs + BN;  // [4 warps][2*BN]
-    for (int c = et; c < BN; c += 128) {
-      ep_sc[c] = d.out_scale ? d.out_scale[d.out_scale_stride ? c : 0] : 1.f;
-      ep_bs[c] = d.bias ? d.bias[c] : 0.f;
-    }
-    bar_sync_epi();
+    float* fold = ep_bs + BN + grp * (4 * 2 * BN);  // [4 warps][2*BN] per group
+    if (grp == 0)
+      for (int c = et; c < BN; c += 128) {
+        ep_sc[c] = d.out_scale ? d.out_scale[d.out_scale_stride ? c : 0] : 1.f;
+        ep_bs[c] = d.bias ? d.bias[c] : 0.f;
+      }
+    asm volatile("bar.sync 3, 256;" ::: "memory");  // both epilogue groups: constants staged
+    auto bar_grp = [&]() {
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
     const bool has_sb = d.out_scale != nullptr || d.bias != nullptr;
     const bool has_stats = d.stats != nullptr;
     const bool has_res = d.res != nullptr;
     const bool need_px = IS3 || (has_res && d.res_mode != IEA_IN_DIRECT);
+    // per-channel scale / bias in registers (smem loads in the tile loop would queue behind the MMA operand reads)
+    constexpr int NREG = NB == 1 ? BN / 2 : 1;  // (32 output channels: the registers go to the statistics instead)
+    float2 esc[NREG], ebs[NREG];
+    if (NB == 1) {
+#pragma unroll
+      for (int j = 0; j < NREG; ++j) { esc[j] = make_float2(ep_sc[2 * j], ep_sc[2 * j + 1]); ebs[j] = make_float2(ep_bs[2 * j], ep_bs[2 * j + 1]); }
+    }
     // (sums are taken on the fp32 values before the bf16 rounding of the store: the rounding error is
     // zero-mean and 2^-9 relative, far below the noise of the batch statistics themselves)
     float2 s1[BN / 2], s2[BN / 2];
@@ -349,23 +393,24 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
           fold[(q * BN + 2 * j) * 2] = s1[j].x; fold[(q * BN + 2 * j) * 2 + 1] = s2[j].x;
           fold[(q * BN + 2 * j + 1) * 2] = s1[j].y; fold[(q * BN + 2 * j + 1) * 2 + 1] = s2[j].y;
         }
-      bar_sync_epi();
+      bar_grp();
       for (int c = et; c < BN * 2; c += 128) {
         const float a = fold[c] + fold[BN * 2 + c] + fold[2 * BN * 2 + c] + fold[3 * BN * 2 + c];
-        d.stats[((int64_t)ev * gridDim.x + blockIdx.x) * BN * 2 + c] = a;
+        d.stats[((int64_t)ev * (2 * gridDim.x) + 2 * blockIdx.x + grp) * BN * 2 + c] = a;
       }
-      bar_sync_epi();
+      bar_grp();
 #pragma unroll
       for (int j = 0; j < BN / 2; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = s1[j]; }
     };
     const int tpe = (int)p.fd_tpe.d;  // macro tiles per event (batch statistics are per event)
-    int ev = (int)fdiv((unsigned)g0, p.fd_tpe), ev_pos = g0 - ev * tpe;
-    Pos c = pos_of(p, g0);
+    int ev = (int)fdiv((unsigned)(g0 + grp), p.fd_tpe), ev_pos = g0 + grp - ev * tpe;
+    Pos c = pos_of(p, g0 + grp);
     const int er = et >> 3, ec = et & 7;
     bf16* const yb = (bf16*)d.y;
     const bf16* const rp = (const bf16*)d.res;
-    for (int t = 0; t < my_n; ++t) {
-      const uint32_t ab = t & 1, aph = (t >> 1) & 1;
+    bool any = false;
+    for (int t = grp; t < my_n; t += 2) {
+      const uint32_t ab = t & 3, aph = (t >> 2) & 1;
       int m0, oh = 0, ow0 = 0;
       const int nn = c.n;
       if (IS3) {
@@ -375,38 +420,57 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
         m0 = (g0 + t) * (BM * MT) + et;
       }
       pos_next(p, c);
+      pos_next(p, c);
       if (has_stats) {
-        if (ev_pos == tpe) { flush(ev); ++ev; ev_pos = 0; }
-        ++ev_pos;
+        if (ev_pos >= tpe) { if (any) flush(ev); ++ev; ev_pos -= tpe; }
+        ev_pos += 2;
+        any = true;
       }
+      if (et == 0) TRACE(5, t);
       mbar_wait(tfull0 + 8 * ab, aph);
       tc_fence_after();
+      if (et == 0) TRACE(6, t);
+      // TMEM -> registers in batches of GRP sub-tiles: the loads are issued back to back and waited for
+      // once, and the sub-tiles of a batch are independent instruction streams
+      constexpr int GRP = NB == 1 ? (MT < 2 ? MT : 2) : 1;
 #pragma unroll
-      for (int sb = 0; sb < MT; ++sb) {
-        const int m = m0 + (IS3 ? sb * 8 : sb * BM);
-        const bool valid = IS3 || m < p.M;
-        int rn = nn, roh = oh, row = ow0 + sb * 8;
-        if (!IS3 && need_px && valid) {
-          const unsigned t1 = fdiv((unsigned)m, p.fd_w);
-          row = (int)((unsigned)m - t1 * (unsigned)d.w); rn = (int)fdiv(t1, p.fd_h); roh = (int)(t1 - (unsigned)rn * (unsigned)d.h);
-        }
+      for (int sg = 0; sg < MT; sg += GRP) {
+        uint32_t raw[GRP][NB][16];
 #pragma unroll
-        for (int cb = 0; cb < NB; ++cb) {
-          uint32_t raw[16];
-          tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + ab * (MT * BN) + sb * BN + cb * 16, raw);
-          tmem_ld_wait();
-          if (valid) {  // (no early `continue`: all lanes must reconverge before the next aligned tcgen05.ld)
+        for (int u = 0; u < GRP; ++u)
+#pragma unroll
+          for (int cb = 0; cb < NB; ++cb)
+            tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + ab * (MT * BN) + (sg + u) * BN + cb * 16, raw[u][cb]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < GRP; ++u) {
+          const int sb = sg + u;
+          const int m = m0 + (IS3 ? sb * 8 : sb * BM);
+          const bool valid = IS3 || m < p.M;
+          if (!valid) continue;  // (the aligned tcgen05.ld of this batch are already done)
+          int rn = nn, roh = oh, row = ow0 + sb * 8;
+          if (!IS3 && need_px) {
+            const unsigned t1 = fdiv((unsigned)m, p.fd_w);
+            row = (int)((unsigned)m - t1 * (unsigned)d.w); rn = (int)fdiv(t1, p.fd_h); roh = (int)(t1 - (unsigned)rn * (unsigned)d.h);
+          }
+#pragma unroll
+          for (int cb = 0; cb < NB; ++cb) {
             const int c0 = cb * 16;
             float2 v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+            for (int j = 0; j < 8; ++j) v[j] = make_float2(__uint_as_float(raw[u][cb][2 * j]), __uint_as_float(raw[u][cb][2 * j + 1]));
             if (has_sb) {
+              if (NB == 1) {
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
-                const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
-                v[2 * j4] = ffma2(v[2 * j4], make_float2(s4.x, s4.y), make_float2(b4.x, b4.y));
-                v[2 * j4 + 1] = ffma2(v[2 * j4 + 1], make_float2(s4.z, s4.w), make_float2(b4.z, b4.w));
+                for (int j = 0; j < 8; ++j) v[j] = ffma2(v[j], esc[j % NREG], ebs[j % NREG]);
+              } else {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
+                  const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
+                  v[2 * j4] = ffma2(v[2 * j4], make_float2(s4.x, s4.y), make_float2(b4.x, b4.y));
+                  v[2 * j4 + 1] = ffma2(v[2 * j4 + 1], make_float2(s4.z, s4.w), make_float2(b4.z, b4.w));
+                }
               }
             }
             if (has_res && c0 < d.res_c) {
@@ -447,9 +511,11 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
             uint32_t o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = pack2(v[j].x, v[j].y);
-            yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            if (has_stats) {
+            if (!(p.dbg & 4)) {
+              yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+              yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+            if (has_stats && !(p.dbg & 8)) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { s1[cb * 8 + j] = fadd2(s1[cb * 8 + j], v[j]); s2[cb * 8 + j] = ffma2(v[j], v[j], s2[cb * 8 + j]); }
             }
@@ -457,9 +523,11 @@ __global__ void __maxnreg__(112) conv_thin_kernel(const __grid_constant__ Params
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty0 + 8 * ab);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
+      if (et == 0) TRACE(7, t);
     }
-    if (has_stats && my_n > 0) flush(ev);
+    if (has_stats && any) flush(ev);
   }
   tc_fence_before();
   __syncthreads();
@@ -509,6 +577,7 @@ static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint
   using G = thin::Geo<CPR, IS3, MT>;
   p.d = *d;
   p.wtc = (const bf16*)d->wpack_tc;
+  { const char* e_ = getenv("IEA_TC2_DBG"); p.dbg = e_ ? atoi(e_) : 0; }  // profiling ablations only
   p.M = (int)(d->n * (int64_t)d->h * d->w);
   p.hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : d->h;
   p.ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : d->w;
@@ -528,27 +597,24 @@ static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint
   const int taps = IS3 ? 9 : 1;
   p.w_bytes = (uint32_t)(d->cout * d->cin * taps * 2);
   p.stage_off = (p.w_bytes + 127) / 128 * 128;
-  const uint32_t misc = (2 * d->cout + 4 * 2 * d->cout) * 4;  // scale, bias, statistics fold
+  const uint32_t misc = (2 * d->cout + 2 * 4 * 2 * d->cout) * 4;  // scale, bias, statistics fold of both groups
   const uint32_t tail = misc + 256;
-  int stages = 4;
-  while (stages > 2 && p.stage_off + stages * G::STAGE + tail > 110 * 1024) --stages;
+  int stages = 8;  // even: the two producer groups own alternate ring slots
+  while (stages > 4 && p.stage_off + stages * G::STAGE + tail > 200 * 1024) stages -= 2;
   p.stages = stages;
-  p.depth = stages >= 4 ? 3 : 2;
-  if (stages == 2) p.depth = 2;
+  p.depth = stages >= 8 ? 3 : 2;  // items each group keeps in flight (it owns stages/2 slots)
   p.misc_off = p.stage_off + stages * G::STAGE;
   p.bar_off = (p.misc_off + misc + 15) / 16 * 16;
   smem = p.bar_off + 256;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * MT * d->cout)) cols <<= 1;
+  while (cols < (uint32_t)(4 * MT * d->cout)) cols <<= 1;
   p.tmem_cols = cols;
   IEA_CHECK_ARG(smem <= 220 * 1024 && cols <= 512, "iea_conv_fprop(tcgen05 thin): tile does not fit (cin=%d cout=%d k=%d)",
                 d->cin, d->cout, d->ksize);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int occ = (smem <= 110 * 1024 && cols <= 256) ? 2 : 1;
-  const int cap = sms * occ;
-  grid = p.n_macro < cap ? p.n_macro : cap;
+  grid = p.n_macro < sms ? p.n_macro : sms;
   return 0;
 }
 
@@ -583,9 +649,15 @@ static int thin_dispatch(const iea_conv_desc* d, cudaStream_t s, int* grid_only)
 }
 
 int iea_conv_fprop_thin(const iea_conv_desc* d, cudaStream_t s) { return thin_dispatch(d, s, nullptr); }
-// statistics slots per event = CTAs of the launch (each CTA folds its run of tiles per event)
+// statistics slots per event = 2 x CTAs of the launch (each epilogue group folds its tiles per event)
 int iea_conv_thin_stats_slots(const iea_conv_desc* d) {
   int grid = 0;
   if (thin_dispatch(d, nullptr, &grid)) return 0;
-  return grid;
+  return 2 * grid;
 }
+
+#ifdef IEA_THIN_TRACE
+extern "C" int iea_debug_thin_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, thin::g_trace, sizeof(long long) * 8 * 512);
+}
+#endif

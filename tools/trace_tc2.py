@@ -10,13 +10,14 @@ r = bench.top_kernel_roofline(E_, 4, 6556.2, "measured")
 print("RESULT", r["ms_per_launch"], r["achieved"])
 buf = (ctypes.c_longlong * (8 * 512))()
 lib = ctypes.CDLL(L.LIB_PATH)
-print("rc", lib.iea_debug_tc2_trace(buf))
+fn = getattr(lib, "iea_debug_thin_trace", None) or lib.iea_debug_tc2_trace
+print("rc", fn(buf))
 t = [[buf[s * 512 + i] for i in range(512)] for s in range(8)]
 t0 = min(x for x in t[0][:8] if x)
 names = ["landed", "xformed", "arrived", "mma_full", "mma_commit", "epi_wait", "epi_full", "epi_done"]
 print("tile " + " ".join("%10s" % n for n in names))
-for i in list(range(0, 24)) + list(range(96, 120)):
+for i in list(range(0, 12)) + list(range(30, 60)):
     print("%4d " % i + " ".join("%10d" % (t[s][i] - t0) for s in range(8)))
 for s in range(8):
-    d = [t[s][i + 1] - t[s][i] for i in range(40, 160)]
+    d = [t[s][i + 1] - t[s][i] for i in range(20, 60)]
     print(names[s], "mean delta per item", sum(d) / len(d))
