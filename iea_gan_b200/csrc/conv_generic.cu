@@ -504,17 +504,58 @@ extern "C" int iea_conv_input_bwd(const iea_conv_desc* d, const void* da, int da
   return check_launch("iea_conv_input_bwd");
 }
 
-extern "C" int iea_conv_out_bwd(const void* dy, int dy_dtype, int dy_ld, const void* y, int y_dtype, int y_ld,
-                                int act, const float* ds1, const float* ds2, int64_t rows, int rows_per_event,
-                                int c, void* g, int g_dtype, iea_stream_t stream) {
-  conv_out_bwd_kernel<<<ew_blocks(rows * c), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, dy_ld, y, y_dtype, y_ld,
-                                                                             act, ds1, ds2, rows, rows_per_event, c,
-                                                                             g, g_dtype);
-  return check_launch("iea_conv_out_bwd");
-}
-
 // ---- vectorised (bf16, 8 channels per 16-byte load) versions of the two bandwidth-bound adjoints ----
 namespace {
+__device__ __forceinline__ uint4 ld_nc16(const bf16* p) {  // streaming 16-byte load (read once: keep it out of L1)
+  uint4 q;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p));
+  return q;
+}
+// g = dy*act' + ds1 + 2*y*ds2 on bf16 rows, one thread per (row, 8 channels), two rows in flight
+__global__ void __launch_bounds__(256) conv_out_bwd_vec(const bf16* dy, int dy_ld, const bf16* y, int y_ld, int act,
+                                                        const float* ds1, const float* ds2, int64_t rows,
+                                                        int rows_per_event, int c, bf16* gout) {
+  const int cgs = c >> 3;
+  const int cgi = (int)(threadIdx.x % cgs), rl = (int)(threadIdx.x / cgs), rpb = 256 / cgs;  // 256 % cgs == 0
+  const bool need_y = act == IEA_ACT_TANH || ds2 != nullptr;
+  const int64_t stride = (int64_t)gridDim.x * rpb;
+  for (int64_t m0 = (int64_t)blockIdx.x * rpb + rl; m0 < rows; m0 += 2 * stride) {
+    uint4 qd[2], qy[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t m = m0 + u * stride;
+      ok[u] = m < rows;
+      if (ok[u]) {
+        qd[u] = ld_nc16(dy + m * dy_ld + cgi * 8);
+        if (need_y) qy[u] = ld_nc16(y + m * y_ld + cgi * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      const int64_t m = m0 + u * stride;
+      float v[8], yv[8];
+      unpack8v(qd[u], v);
+      if (need_y) unpack8v(qy[u], yv);
+      if (act == IEA_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= (1.f - yv[j] * yv[j]);
+      }
+      if (ds1) {
+        const int64_t e = m / rows_per_event;
+        const float4* a1 = reinterpret_cast<const float4*>(ds1 + e * c + cgi * 8);
+        const float4* a2 = reinterpret_cast<const float4*>(ds2 + e * c + cgi * 8);
+        const float4 s0 = a1[0], s1 = a1[1], t0 = a2[0], t1 = a2[1];
+        const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += fmaf(2.f * yv[j], t[j], s[j]);
+      }
+      *reinterpret_cast<uint4*>(gout + m * c + cgi * 8) = pack8v(v);
+    }
+  }
+}
 __global__ void __launch_bounds__(256) colsum_part_vec(const bf16* g, int g_ld, int64_t rows, int c, float* part,
                                                        int64_t rows_per_block) {
   extern __shared__ float red[];  // [lanes][c]
@@ -525,13 +566,27 @@ __global__ void __launch_bounds__(256) colsum_part_vec(const bf16* g, int g_ld, 
   float a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = 0.f;
-  if (pl < lanes)
-    for (int64_t m = r0 + pl; m < r1; m += lanes) {
+  if (pl < lanes) {
+    int64_t m = r0 + pl;
+    for (; m + 3 * lanes < r1; m += 4 * lanes) {  // four independent 16-byte loads in flight per thread
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = ld_nc16(g + (m + u * lanes) * g_ld + cgi * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8v(q[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += f[j];
+      }
+    }
+    for (; m < r1; m += lanes) {
       float f[8];
-      unpack8v(*reinterpret_cast<const uint4*>(g + m * g_ld + cgi * 8), f);
+      unpack8v(ld_nc16(g + m * g_ld + cgi * 8), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] += f[j];
     }
+  }
   if (pl < lanes)
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[pl * c + cgi * 8 + j] = a[j];
@@ -622,3 +677,22 @@ extern "C" int iea_residual_bwd(const void* g, int g_dtype, int g_ld, int64_t n,
       g, g_dtype, g_ld, n, h, w, res_c, res_mode, dres, dres_dtype, dres_ld, dres_c, beta);
   return check_launch("iea_residual_bwd");
 }
+
+extern "C" int iea_conv_out_bwd(const void* dy, int dy_dtype, int dy_ld, const void* y, int y_dtype, int y_ld,
+                                int act, const float* ds1, const float* ds2, int64_t rows, int rows_per_event,
+                                int c, void* g, int g_dtype, iea_stream_t stream) {
+  if (dy_dtype == IEA_BF16 && y_dtype == IEA_BF16 && g_dtype == IEA_BF16 && c % 8 == 0 && 256 % (c / 8) == 0 &&
+      dy_ld % 8 == 0 && y_ld % 8 == 0 && al16(dy) && al16(y) && al16(g)) {
+    const int rpb = 256 / (c / 8);
+    int64_t blocks = (rows + 2 * rpb - 1) / (2 * rpb);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    conv_out_bwd_vec<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, dy_ld, (const bf16*)y, y_ld, act, ds1,
+                                                                   ds2, rows, rows_per_event, c, (bf16*)g);
+    return check_launch("iea_conv_out_bwd(vec)");
+  }
+  conv_out_bwd_kernel<<<ew_blocks(rows * c), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, dy_ld, y, y_dtype, y_ld,
+                                                                             act, ds1, ds2, rows, rows_per_event, c,
+                                                                             g, g_dtype);
+  return check_launch("iea_conv_out_bwd");
+}
+

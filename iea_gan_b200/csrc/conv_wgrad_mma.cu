@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
       const int r = e / p.cpg, c = e - r * p.cpg;
       int64_t m;
       bool in = true;
-      if (IS3) m = ((int64_t)o.n * d.h + o.h0 + (r >> 3)) * d.w + o.w0 + (r & 7);
-      else { m = o.m0 + r; in = m < p.M; }
+      if (IS3) {  // (images smaller than / not a multiple of the 16x8 tile: rows and columns beyond the edge are zero)
+        m = ((int64_t)o.n * d.h + o.h0 + (r >> 3)) * d.w + o.w0 + (r & 7);
+        in = o.h0 + (r >> 3) < d.h && o.w0 + (r & 7) < d.w;
+      } else { m = o.m0 + r; in = m < p.M; }
       const uint32_t dst = s0 + p.g_off + c * p.plane_g + r * 16;
       if (!in) { asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0) : "memory"); continue; }
       if (thin_g) {
@@ -322,11 +324,11 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   if (d->in_mode == IEA_IN_POOL2 && (d->ksize != 1 || thin_a)) return 0;
   const int cin_eff = thin_a ? 16 : d->cin, cout_eff = thin_g ? 16 : d->cout;
   const bool is3 = d->ksize == 3;
-  if (is3 && (d->h % 16 || d->w % 8)) return 0;
+  if (is3 && d->in_mode == IEA_IN_UP2 && (d->h % 2 || d->w % 2)) return 0;
   if (!is3 && (((int64_t)d->h * d->w) % 128) && d->in_scale) return 0;  // a tile must not straddle images
   if (!is3 && d->in_mode == IEA_IN_UP2) return 0;
   const int64_t M = d->n * (int64_t)d->h * d->w;
-  if (M >= (1ll << 31) || M < 1024) return 0;  // tiny problems stay on the generic kernel
+  if (M >= (1ll << 31) || M < 512) return 0;  // tiny problems stay on the generic kernel
   const int taps = d->ksize * d->ksize;
   const int npix = is3 ? wg::PH * wg::PW : 128;
   const uint32_t plane_a = (npix * 16 + 127) / 128 * 128, plane_g = 128 * 16;
@@ -348,8 +350,8 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   p->hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : (d->in_mode == IEA_IN_POOL2 ? d->h * 2 : d->h);
   p->ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : (d->in_mode == IEA_IN_POOL2 ? d->w * 2 : d->w);
   p->fd_w = wg::make_fastdiv(d->w); p->fd_h = wg::make_fastdiv(d->h);
-  p->tiles_w = is3 ? d->w / 8 : 1;
-  p->tiles_h = is3 ? d->h / 16 : 1;
+  p->tiles_w = is3 ? (d->w + 7) / 8 : 1;    // edge tiles are masked (8x8 / 4x4 layers: one partly filled tile per image)
+  p->tiles_h = is3 ? (d->h + 15) / 16 : 1;
   p->n_tiles = (int)(is3 ? d->n * (int64_t)p->tiles_w * p->tiles_h : (M + 127) / 128);
   p->fd_tw = wg::make_fastdiv(p->tiles_w); p->fd_th = wg::make_fastdiv(p->tiles_h);
   p->fd_hw = wg::make_fastdiv(d->h * d->w);

@@ -40,9 +40,29 @@ def conv_impl():
 LAUNCHES = [0]  # kernels launched through the C ABI (bench.py reports it)
 
 
+PROFILE = None  # tools/prof_layers.py sets this to a list: (name, tag, start event, end event) per C-ABI call
+
+
+def _tag(name, args):
+    """Shape tag of a call for the per-layer profile (convolution descriptors carry their geometry)."""
+    a0 = getattr(args[0], "_obj", None) if args else None
+    if isinstance(a0, L.ConvDesc):
+        return "n%d %dx%d %d->%d k%d in%d%s%s%s%s" % (a0.n, a0.h, a0.w, a0.cin, a0.cout, a0.ksize, a0.in_mode,
+                                                    " aff" if a0.in_scale else "", " relu" if a0.in_relu else "",
+                                                    " res%d" % a0.res_mode if a0.res else "", " st" if a0.stats else "")
+    return " ".join(str(a) for a in args if isinstance(a, int) and 0 <= a < (1 << 31))[:48]
+
+
 def K(name, *args, launches=1):
     LAUNCHES[0] += launches
-    return call(name, *args)
+    if PROFILE is None:
+        return call(name, *args)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rc = call(name, *args)
+    b.record()
+    PROFILE.append((name, _tag(name, args), a, b))
+    return rc
 
 
 def cdiv(a, b):

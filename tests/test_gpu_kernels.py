@@ -313,7 +313,9 @@ def _tc_vs_generic(eng, variant, cin, cout, k, mode, relu, aff, resm, hw, n):
 @pytest.mark.parametrize("cin,cout,k,hw,gdt", [(1, 32, 3, (32, 32), "bf16"), (32, 1, 3, (32, 32), "fp32"),
                                               (128, 32, 1, (16, 16), "bf16"), (64, 128, 1, (16, 16), "bf16"),
                                               (128, 128, 3, (16, 16), "bf16"), (512, 128, 1, (8, 8), "bf16"),
-                                              (128, 512, 1, (8, 8), "bf16"), (256, 64, 1, (16, 16), "bf16")])
+                                              (128, 512, 1, (8, 8), "bf16"), (256, 64, 1, (16, 16), "bf16"),
+                                              (128, 128, 3, (8, 8), "bf16"), (128, 128, 3, (4, 4), "bf16"),
+                                              (32, 16, 3, (12, 20), "bf16")])
 def test_wgrad_mma_thin_and_wide(eng, cin, cout, k, hw, gdt):
     """The 1-channel stem / output convs (zero-extended operands) and the many-block 1x1 shapes of the
     tensor-core weight-gradient kernel against the CUDA-core kernel."""
