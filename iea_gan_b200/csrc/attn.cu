@@ -3,10 +3,12 @@
 // HBM; forward keeps a running max / sum per query and saves only the log-sum-exp.  Backward is two
 // deterministic passes (query-parallel for d theta, key-parallel for d phi / d g), no atomics.
 //   theta [n][hw][ck], phi [n][hwk][ck], g [n][hwk][cv]  ->  o [n][hw][cv]
-// First (CUDA-core) version; the tcgen05 version of the two GEMMs is the next step.
+// CUDA-core version for odd shapes / fp32 activations; the shipped shape (ck 32, cv 128, bf16) runs on the
+// tcgen05 kernels of attn_tc.cu.
 #include "common.cuh"
 using namespace iea;
 
+static inline bool tc_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 namespace {
 constexpr int QT = 32;   // queries per block
 constexpr int KT = 64;   // keys per smem tile (forward / pass A)
@@ -228,9 +230,18 @@ __global__ void __launch_bounds__(256) attn_bwd_kv_kernel(const void* d_o, const
 }
 }  // namespace
 
+int iea_attn_tc_ok(int dtype, int64_t n, int hw, int hwk, int ck, int cv, const void* a, const void* b, const void* c,
+                   const void* d);
+int iea_attn_fwd_tc(const void* theta, const void* phi, const void* g, int64_t n, int hw, int hwk, void* o, float* lse,
+                    cudaStream_t s);
+int iea_attn_bwd_tc(const void* d_o, const void* theta, const void* phi, const void* g, const void* o, const float* lse,
+                    int64_t n, int hw, int hwk, void* dtheta, void* dphi, void* dg, float* dq, cudaStream_t s);
+
 extern "C" int iea_attn_fwd(const void* theta, const void* phi, const void* g, int dtype, int64_t n, int hw, int hwk,
                             int ck, int cv, void* o, float* lse, iea_stream_t stream) {
   IEA_CHECK_ARG(ck <= 32 && cv <= 128 && ck > 0 && cv > 0, "iea_attn_fwd: ck=%d cv=%d outside the built range", ck, cv);
+  if (iea_attn_tc_ok(dtype, n, hw, hwk, ck, cv, theta, phi, g, o))
+    return iea_attn_fwd_tc(theta, phi, g, n, hw, hwk, o, lse, (cudaStream_t)stream);
   size_t smem = (size_t)(QT * (ck + 1) + KT * (ck + 1) + KT * cv) * sizeof(float);
   IEA_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(hw, QT), (unsigned)n);
@@ -242,6 +253,8 @@ extern "C" int iea_attn_bwd(const void* d_o, const void* theta, const void* phi,
                             const float* lse, int dtype, int64_t n, int hw, int hwk, int ck, int cv, void* dtheta,
                             void* dphi, void* dg, float* dq_scratch, iea_stream_t stream) {
   IEA_CHECK_ARG(ck <= 32 && cv <= 128 && ck > 0 && cv > 0, "iea_attn_bwd: ck=%d cv=%d outside the built range", ck, cv);
+  if (iea_attn_tc_ok(dtype, n, hw, hwk, ck, cv, theta, phi, g, o) && tc_al16(d_o) && tc_al16(dtheta) && tc_al16(dphi) && tc_al16(dg))
+    return iea_attn_bwd_tc(d_o, theta, phi, g, o, lse, n, hw, hwk, dtheta, dphi, dg, dq_scratch, (cudaStream_t)stream);
   cudaStream_t s = (cudaStream_t)stream;
   size_t sa = (size_t)(QT * (ck + 1) + QT * (cv + 1) + 32 * (ck + 1) + 32 * (cv + 1)) * sizeof(float);
   IEA_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa));

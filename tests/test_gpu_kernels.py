@@ -340,3 +340,40 @@ def test_wgrad_mma_thin_and_wide(eng, cin, cout, k, hw, gdt):
     L.call("iea_conv_wgrad", C.byref(d), g.data_ptr(), L.dt(g), cout, ref.data_ptr(), 8, L.stream())
     torch.cuda.synchronize()
     assert rel(gp[0], ref.sum(0)) < 5e-3  # slice 0 = fixed-order sum of the per-CTA partials
+
+
+@pytest.mark.parametrize("n,hw,hwk", [(40, 1024, 256), (6, 3072, 768), (3, 128, 128)])
+def test_attention_tcgen05_vs_torch(eng, n, hw, hwk):
+    """BigGAN attention core (layers.py:289-299) on the tcgen05 kernels (attn_tc.cu) at the shipped
+    channel counts (ck 32, cv 128): forward, lse and the three input gradients against torch fp32 on the
+    same bf16 inputs, and against the CUDA-core kernels.  Tolerance: P and dS are rounded to bf16
+    before their second GEMM (2^-9 relative per element) and the outputs are bf16."""
+    dev = "cuda"
+    ck, cv = 32, 128
+    torch.manual_seed(11)
+    th = (torch.randn(n, hw, ck, device=dev) * 0.7).bfloat16()
+    ph = (torch.randn(n, hwk, ck, device=dev) * 0.7).bfloat16()
+    gv = torch.randn(n, hwk, cv, device=dev).bfloat16()
+    go = torch.randn(n, hw, cv, device=dev).bfloat16()
+    tr, pr, gr = (t.float().requires_grad_(True) for t in (th, ph, gv))
+    beta = F.softmax(tr @ pr.transpose(1, 2), dim=-1)
+    o_ref = beta @ gr
+    o_ref.backward(go.float())
+    lse_ref = torch.logsumexp(tr.detach() @ pr.detach().transpose(1, 2), dim=-1)
+    outs = {}
+    try:
+        for impl in ("tcgen05", "generic"):
+            os.environ["IEA_ATTN_IMPL"] = impl
+            tape = eng.Tape(True)
+            tv, pv, gvv = eng.Var(th), eng.Var(ph), eng.Var(gv)
+            ov = eng.attn_core(tape, tv, pv, gvv, n, hw, hwk, ck, cv)
+            ov.g = go
+            tape.backward()
+            torch.cuda.synchronize()
+            outs[impl] = (ov.t.float(), tv.g.float(), pv.g.float(), gvv.g.float())
+    finally:
+        os.environ.pop("IEA_ATTN_IMPL", None)
+    refs = (o_ref, tr.grad, pr.grad, gr.grad)
+    for name, got, ref, gen in zip(("o", "dtheta", "dphi", "dg"), outs["tcgen05"], refs, outs["generic"]):
+        assert rel(got, ref) < 1.5e-2, name
+        assert rel(got, gen) < 1.5e-2, name
