@@ -357,8 +357,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
     float* fold = ep_bs + BN + grp * (4 * 2 * BN);  // [4 warps][2*BN] per group
     if (grp == 0)
       for (int c = et; c < BN; c += 128) {
-        ep_sc[c] = d.out_scale ? d.out_scale[d.out_scale_stride ? c : 0] : 1.f;
-        ep_bs[c] = d.bias ? d.bias[c] : 0.f;
+        ep_sc[c] = d.out_scale ? d.out_scale[d.out_scale_stride && c < d.cout ? c : 0] : 1.f;
+        ep_bs[c] = d.bias && c < d.cout ? d.bias[c] : 0.f;
       }
     asm volatile("bar.sync 3, 256;" ::: "memory");  // both epilogue groups: constants staged
     auto bar_grp = [&]() {
@@ -494,6 +494,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
                 for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
               }
             }
+            if (NB == 1 && d.cout == 1) {  // padded output conv: one real channel
+              float v0 = v[0].x;
+              if (d.act == IEA_ACT_RELU) v0 = fmaxf(v0, 0.f);
+              else if (d.act == IEA_ACT_TANH) v0 = tanhf(v0);
+              st_act(d.y, d.y_dtype, (int64_t)m * d.y_ld, v0);
+              continue;
+            }
             uint4* yp = reinterpret_cast<uint4*>(yb + (int64_t)m * d.y_ld + c0);
             if (d.acc_c0 >= 0 && c0 >= d.acc_c0) {
               const uint4 r0 = yp[0], r1 = yp[1];
@@ -543,11 +550,15 @@ int iea_conv_tc_base_ok(const iea_conv_desc* d, int padded);
 
 // macro-tile width (in 16x8 / 128-pixel tiles) the kernel uses for this layer; 0: layer not eligible
 static int thin_mt(const iea_conv_desc* d) {
-  if (!iea_conv_tc_base_ok(d, 0)) return 0;
+  if (!iea_conv_tc_base_ok(d, d->cout == 1 ? 1 : 0)) return 0;
   { const char* e_ = getenv("IEA_THIN"); if (e_ && e_[0] == '0') return 0; }  // profiling switch: old kernels only
-  if (d->cout != 16 && d->cout != 32) return 0;
+  // (cout 1 with a 16-row weight pack: the generator's 32->1 output conv; its real channel is stored
+  //  straight from the accumulator registers in the storage type of y)
+  const bool pad1 = d->cout == 1 && d->cout_tc == 16;
+  if (d->cout != 16 && d->cout != 32 && !pad1) return 0;
   if (d->cin != 16 && d->cin != 32 && d->cin != 64) return 0;
-  if (d->y_dtype != IEA_BF16 || d->cin < 16) return 0;
+  if ((!pad1 && d->y_dtype != IEA_BF16) || d->cin < 16) return 0;
+  if (pad1 && (d->stats || d->res || d->acc_c0 >= 0)) return 0;
   if (d->in_mode == IEA_IN_POOL2) return 0;
   const int64_t M = d->n * (int64_t)d->h * d->w;
   if (M >= (1ll << 31) || M * (int64_t)(d->x_ld > d->y_ld ? d->x_ld : d->y_ld) >= (1ll << 40)) return 0;
@@ -595,9 +606,10 @@ static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint
   const int64_t per_event = IS3 ? 40ll * p.mtw * p.mth : (40ll * hw) / (128 * MT);
   p.fd_tpe = thin::make_fastdiv(per_event > 0 ? (uint32_t)per_event : 1u);
   const int taps = IS3 ? 9 : 1;
-  p.w_bytes = (uint32_t)(d->cout * d->cin * taps * 2);
+  const int cout_e = d->cout == 1 ? 16 : d->cout;  // rows of the weight pack / accumulator columns
+  p.w_bytes = (uint32_t)(cout_e * d->cin * taps * 2);
   p.stage_off = (p.w_bytes + 127) / 128 * 128;
-  const uint32_t misc = (2 * d->cout + 2 * 4 * 2 * d->cout) * 4;  // scale, bias, statistics fold of both groups
+  const uint32_t misc = (2 * cout_e + 2 * 4 * 2 * cout_e) * 4;  // scale, bias, statistics fold of both groups
   const uint32_t tail = misc + 256;
   int stages = 8;  // even: the two producer groups own alternate ring slots
   while (stages > 4 && p.stage_off + stages * G::STAGE + tail > 200 * 1024) stages -= 2;
@@ -607,7 +619,7 @@ static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint
   p.bar_off = (p.misc_off + misc + 15) / 16 * 16;
   smem = p.bar_off + 256;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(4 * MT * d->cout)) cols <<= 1;
+  while (cols < (uint32_t)(4 * MT * cout_e)) cols <<= 1;
   p.tmem_cols = cols;
   IEA_CHECK_ARG(smem <= 220 * 1024 && cols <= 512, "iea_conv_fprop(tcgen05 thin): tile does not fit (cin=%d cout=%d k=%d)",
                 d->cin, d->cout, d->ksize);
@@ -631,7 +643,7 @@ static int thin_launch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
 }
 
 static int thin_dispatch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
-  const int mt = thin_mt(d), cpr = d->cin / 8, nb = d->cout / 16;
+  const int mt = thin_mt(d), cpr = d->cin / 8, nb = d->cout == 1 ? 1 : d->cout / 16;
   const bool is3 = d->ksize == 3;
 #define IEA_THIN_CASE(C_, I_, N_, M_) \
   if (cpr == C_ && is3 == I_ && nb == N_ && mt == M_) return thin_launch<C_, I_, N_, M_>(d, s, grid_only);

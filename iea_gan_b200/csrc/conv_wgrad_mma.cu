@@ -371,7 +371,11 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   return 1;
 }
 
+int iea_conv_c1_wgrad_grid(const iea_conv_desc* d, int g_dtype, int g_ld);
+int iea_conv_c1_wgrad(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* parts, cudaStream_t s);
+
 extern "C" int iea_conv_wgrad_mma_slices(const iea_conv_desc* d, int g_dtype, int g_ld) {
+  if (const int c1g = iea_conv_c1_wgrad_grid(d, g_dtype, g_ld)) return c1g + 1;  // 1-channel side: conv_c1.cu
   wg::Params p; int npair;
   if (!wgrad_mma_plan(d, g_dtype, g_ld, &p, &npair)) return 0;
   int dev = 0, sms = 148;
@@ -384,6 +388,14 @@ extern "C" int iea_conv_wgrad_mma_slices(const iea_conv_desc* d, int g_dtype, in
 
 extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* gpart,
                                   iea_stream_t stream) {
+  if (const int c1g = iea_conv_c1_wgrad_grid(d, g_dtype, g_ld)) {
+    const int64_t total = (int64_t)d->cout * 9 * d->cin;
+    int rc = iea_conv_c1_wgrad(d, g, g_dtype, g_ld, gpart + total, (cudaStream_t)stream);
+    if (rc) return rc;
+    int rb = (int)((total + 255) / 256);
+    wg::wgrad_reduce_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>(gpart + total, c1g, total, gpart);
+    return check_launch("iea_conv_wgrad_mma(1-channel)");
+  }
   wg::Params p; int npair;
   IEA_CHECK_ARG(wgrad_mma_plan(d, g_dtype, g_ld, &p, &npair), "iea_conv_wgrad_mma: shape not handled (cin=%d cout=%d k=%d)",
                 d->cin, d->cout, d->ksize);
