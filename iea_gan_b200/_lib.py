@@ -57,7 +57,7 @@ _SIG = {
     "iea_conv_stats_slots": [vp],
     "iea_conv_wgrad": [vp, vp, i32, i32, vp, i32, vp],
     "iea_conv_wgrad_mma_slices": [vp, i32, i32],
-    "iea_conv_wgrad_mma": [vp, vp, i32, i32, vp, vp],
+    "iea_conv_wgrad_mma": [vp, vp, i32, i32, vp, vp, vp],
     "iea_conv_input_bwd": [vp, vp, i32, vp, i32, i32, f32, vp, vp, vp, vp],
     "iea_conv_out_bwd": [vp, i32, i32, vp, i32, i32, i32, vp, vp, i64, i32, i32, vp, i32, vp],
     "iea_colsum": [vp, i32, i32, i64, i32, vp, f32, vp, vp],

@@ -43,6 +43,7 @@ struct Params {
   iea_conv_desc d;
   const void* g; int g_dtype, g_ld;
   float* gpart;
+  float* cs_parts;  // [gridDim.x][cout] column sums of g (bias gradient) or NULL
   int64_t M;
   int n_tiles, tiles_w, tiles_h, hs, ws, cpa, cpg, cin_eff, cout_eff, stages, depth, P, WP;
   int nib_l, ncb_l, gi;  // output split over blockIdx.y: ci blocks / co blocks per CTA, groups along ci
@@ -102,6 +103,15 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[q][t][j][r] = 0.f;
+
+  // bias gradient for free: the g fragments are already in registers, one extra MMA against an all-ones B
+  // fragment per k-step gives sum_px g[px][co] (warps that own the first input-channel block only)
+  const bool cs_cta = p.cs_parts != nullptr && ib0 == 0;
+  float acc_cs[NPAIR][4];
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc_cs[q][r] = 0.f;
 
   // conv-resolution coordinates of patch pixel pp; false = padding / beyond the last row
   auto pix_a = [&](const Origin& o, int pp, int& ih, int& iw, int64_t& m) -> bool {
@@ -242,6 +252,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
       for (int ks = kg; ks < 8; ks += p.WP) {
         uint32_t a[4];
         ldsm_x4_t(s0 + p.g_off + (cb * 2 + (mat & 1)) * p.plane_g + (ks * 16 + (mat >> 1) * 8 + rr) * 16, a[0], a[1], a[2], a[3]);
+        if (cs_cta && ib == 0) mma16816(acc_cs[q], a, 0x3F803F80u, 0x3F803F80u);
         const uint32_t brow = s0 + (ib * 2 + (mat >> 1)) * p.plane_a;
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) {
@@ -271,6 +282,8 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) scr[(pair0 * TAPS * 8 + t * 8 + j * 4 + r) * 32 + lane] = acc[0][t][j][r];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) scr[(p.P * TAPS * 8 + pair0 * 4 + r) * 32 + lane] = acc_cs[0][r];
       }
       __syncthreads();
       if (kg == 0) {
@@ -280,6 +293,8 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[0][t][j][r] += scr[(pair0 * TAPS * 8 + t * 8 + j * 4 + r) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc_cs[0][r] += scr[(p.P * TAPS * 8 + pair0 * 4 + r) * 32 + lane];
       }
       __syncthreads();
     }
@@ -300,6 +315,11 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
           const int ci = ca0 + ib * 16 + j * 8 + 2 * (lane & 3) + (r & 1);
           if (co < d.cout && ci < d.cin) out[((int64_t)co * TAPS + t) * d.cin + ci] = acc[q][t][j][r];
         }
+    if (cs_cta && ib == 0 && (lane & 3) == 0) {  // every column of the ones-MMA holds the same sum
+      const int co = cg0 + cb * 16 + (lane >> 2);
+      if (co < d.cout) p.cs_parts[(int64_t)blockIdx.x * d.cout + co] = acc_cs[q][0];
+      if (co + 8 < d.cout) p.cs_parts[(int64_t)blockIdx.x * d.cout + co + 8] = acc_cs[q][2];
+    }
   }
 }
 
@@ -383,18 +403,21 @@ extern "C" int iea_conv_wgrad_mma_slices(const iea_conv_desc* d, int g_dtype, in
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int occ = p.stages * p.stage_bytes <= 100 * 1024 ? 2 : 1;
   const int grid = p.n_tiles < sms * occ ? p.n_tiles : sms * occ;
-  return grid + 1;  // grid per-CTA partials + one slot for their sum (slice 0 after the call)
+  // grid per-CTA partials + one slot for their sum (slice 0 after the call) + room for the per-CTA
+  // column sums of g (grid * cout floats) behind them
+  const int64_t total = (int64_t)d->cout * d->ksize * d->ksize * d->cin;
+  return grid + 1 + (int)(((int64_t)grid * d->cout + total - 1) / total);
 }
 
 extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* gpart,
-                                  iea_stream_t stream) {
+                                  float* dbias, iea_stream_t stream) {
   if (const int c1g = iea_conv_c1_wgrad_grid(d, g_dtype, g_ld)) {
     const int64_t total = (int64_t)d->cout * 9 * d->cin;
     int rc = iea_conv_c1_wgrad(d, g, g_dtype, g_ld, gpart + total, (cudaStream_t)stream);
     if (rc) return rc;
     int rb = (int)((total + 255) / 256);
     wg::wgrad_reduce_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>(gpart + total, c1g, total, gpart);
-    return check_launch("iea_conv_wgrad_mma(1-channel)");
+    return check_launch("iea_conv_wgrad_mma(1-channel)");  // 0: the bias gradient was not produced
   }
   wg::Params p; int npair;
   IEA_CHECK_ARG(wgrad_mma_plan(d, g_dtype, g_ld, &p, &npair), "iea_conv_wgrad_mma: shape not handled (cin=%d cout=%d k=%d)",
@@ -407,12 +430,13 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
   const int nib_ = p.cin_eff / 16, ncb_ = p.cout_eff / 16;
   uint32_t smem = p.stages * p.stage_bytes;
   const int occ = smem <= 100 * 1024 ? 2 : 1;
-  if (p.WP > 1 && smem < (uint32_t)(p.P * taps_ * 8 * 32 * 4)) smem = p.P * taps_ * 8 * 32 * 4;  // fold scratch
+  if (p.WP > 1 && smem < (uint32_t)(p.P * (taps_ * 8 + 4) * 32 * 4)) smem = p.P * (taps_ * 8 + 4) * 32 * 4;  // fold scratch
   const int grid = p.n_tiles < sms * occ ? p.n_tiles : sms * occ;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t total = (int64_t)d->cout * taps_ * d->cin;
   float* parts = gpart + total;  // slices 1..grid hold the per-CTA partials, slice 0 receives their sum
   p.gpart = parts;
+  p.cs_parts = dbias ? gpart + (int64_t)(grid + 1) * total : nullptr;
   auto launch = [&](auto kern) -> int {
     IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(grid, (nib_ / p.nib_l) * (ncb_ / p.ncb_l)), 256, smem, s>>>(p);
@@ -435,5 +459,7 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
   int rb = (int)((total + 255) / 256);
   if (rb > 592) rb = 592;
   wg::wgrad_reduce_kernel<<<rb, 256, 0, s>>>(parts, grid, total, gpart);
-  return check_launch("iea_conv_wgrad_mma");
+  if (dbias) wg::wgrad_reduce_kernel<<<(d->cout + 255) / 256, 256, 0, s>>>(p.cs_parts, grid, d->cout, dbias);
+  rc = check_launch("iea_conv_wgrad_mma");
+  return rc ? rc : (dbias ? 1 : 0);  // 1: dbias holds the column sums of g
 }

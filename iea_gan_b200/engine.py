@@ -420,11 +420,9 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
             K("iea_conv_out_bwd", g_ptr, dt(g_t), g_ld, yv.off(), dt(y), yv.ld, act, ptr(ds1), ptr(ds2), M, rpe_,
               cout, ptr(geff), dt(geff), L.stream())
             g_t, g_ptr, g_ld = geff, geff.data_ptr(), cout
-        if bias is not None and bias.requires_grad:
-            db = torch.empty(cout, dtype=torch.float32, device=dev)
-            K("iea_colsum", g_ptr, dt(g_t), g_ld, M, cout, ptr(db), 0.0, ptr(_f32(300 * cout, dev)), L.stream(),
-              launches=2)
-            tape.pgrad(bias, db)
+        need_db = bias is not None and bias.requires_grad
+        db = torch.empty(cout, dtype=torch.float32, device=dev) if need_db else None
+        db_done = False
         if res is not None and res.need:
             rg, beta = _accum_target(res)
             K("iea_residual_bwd", g_ptr, dt(g_t), g_ld, n, h, w, res_c, res_mode, res.off(rg), dt(rg), res.ld,
@@ -437,7 +435,9 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
             nsplit = call("iea_conv_wgrad_mma_slices", C.byref(dfw), dt(g_t), g_ld) if conv_impl() != L.IMPL_GENERIC else 0
             if nsplit > 0:  # tensor-core split-K over pixel tiles, one partial per (CTA, k-step group)
                 gpart = torch.empty((nsplit, cout, kdim), dtype=torch.float32, device=dev)
-                K("iea_conv_wgrad_mma", C.byref(dfw), g_ptr, dt(g_t), g_ld, ptr(gpart), L.stream(), launches=2)
+                # (the same pass also sums g over the pixels: the bias gradient, when asked for)
+                db_done = K("iea_conv_wgrad_mma", C.byref(dfw), g_ptr, dt(g_t), g_ld, ptr(gpart), ptr(db), L.stream(),
+                            launches=3 if need_db else 2) == 1
                 gpart, nsplit = gpart[:1], 1  # slice 0 now holds the sum of the per-CTA partials
             else:
                 nsplit = max(1, min(64, M // 4096))
@@ -452,6 +452,11 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
                       ptr(dw), 0.0, l.rows, l.cin, l.taps, ptr(_f32(520, dev)), L.stream(), launches=2)
                     tape.pgrad(l.weight, dw)
                 r0 += l.rows
+        if need_db:
+            if not db_done:
+                K("iea_colsum", g_ptr, dt(g_t), g_ld, M, cout, ptr(db), 0.0, ptr(_f32(300 * cout, dev)), L.stream(),
+                  launches=2)
+            tape.pgrad(bias, db)
         plain = in_mode == L.IN_DIRECT and not in_relu and ss is None and xv.c == xv.ld
         if xv.need and plain:
             xg, beta = _accum_target(xv)

@@ -118,10 +118,13 @@ int iea_conv_wgrad(const iea_conv_desc* d /* host; x/T fields and geometry are u
 /* tensor-core (mma.sync m16n8k16) split-K weight gradient for the thin high-resolution layers.
  * iea_conv_wgrad_mma_slices returns the number of partial slices the kernel will write for this shape
  * (0: shape not handled -> use iea_conv_wgrad); gpart must hold slices*cout*taps*cin floats.  On return
- * slice 0 holds the fixed-order sum of the per-CTA partials (pass it to iea_sn_weight_bwd with nsplit 1). */
+ * slice 0 holds the fixed-order sum of the per-CTA partials (pass it to iea_sn_weight_bwd with nsplit 1).
+ * dbias != NULL asks for the bias gradient sum_px g[px][co] from the same pass (one extra MMA per k-step
+ * on the g fragments already in registers); returns 1 when dbias was written, 0 when the shape's kernel
+ * does not produce it (the caller then runs iea_colsum), < 0 on error. */
 int iea_conv_wgrad_mma_slices(const iea_conv_desc* d /* host */, int g_dtype, int g_ld);
 int iea_conv_wgrad_mma(const iea_conv_desc* d /* host */, const void* g, int g_dtype, int g_ld, float* gpart,
-                       iea_stream_t stream);
+                       float* dbias /* [cout] or NULL */, iea_stream_t stream);
 
 /* backward of T: da [n][h][w][cin] (at conv resolution) -> dx at x's resolution and the
  * per-(n,c) reductions dscale = sum da*relu'*x, dshift = sum da*relu'.  beta=1 accumulates dx. */

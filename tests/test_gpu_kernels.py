@@ -335,11 +335,14 @@ def test_wgrad_mma_thin_and_wide(eng, cin, cout, k, hw, gdt):
     slices = L.call("iea_conv_wgrad_mma_slices", C.byref(d), L.dt(g), cout)
     assert slices > 0
     gp = torch.empty(slices, cout, k * k * cin, device=dev)
-    L.call("iea_conv_wgrad_mma", C.byref(d), g.data_ptr(), L.dt(g), cout, gp.data_ptr(), L.stream())
+    db = torch.full((cout,), float("nan"), device=dev)
+    fused = L.call("iea_conv_wgrad_mma", C.byref(d), g.data_ptr(), L.dt(g), cout, gp.data_ptr(), db.data_ptr(), L.stream())
     ref = torch.empty(8, cout, k * k * cin, device=dev)
     L.call("iea_conv_wgrad", C.byref(d), g.data_ptr(), L.dt(g), cout, ref.data_ptr(), 8, L.stream())
     torch.cuda.synchronize()
     assert rel(gp[0], ref.sum(0)) < 5e-3  # slice 0 = fixed-order sum of the per-CTA partials
+    if fused:  # bias gradient from the same pass (ones-column MMA on the g fragments)
+        assert rel(db, g.float().reshape(-1, cout).sum(0)) < 2e-3
 
 
 @pytest.mark.parametrize("n,hw,hwk", [(40, 1024, 256), (6, 3072, 768), (3, 128, 128)])
