@@ -65,6 +65,14 @@ __device__ long long g_trace[8][512];
 #define TRACE(slot, idx) do { } while (0)
 #endif
 
+// ablation switches of the profiling builds (-DIEA_THIN_DBG: IEA_TC2_DBG bits 1 no prologue transform, 2 no MMA,
+// 4 no output stores, 8 no statistics, 16 no loads); compiled out of the product kernel
+#ifdef IEA_THIN_DBG
+#define DBG(bit) (p.dbg & (bit))
+#else
+#define DBG(bit) 0
+#endif
+
 struct Params {
   iea_conv_desc d;
   const bf16* wtc;
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
     };
     auto issue = [&](const Cur& c) {
       mbar_wait(empty0 + 8 * c.s, c.ph ^ 1);
-      if (p.dbg & 16) return;
+      if (DBG(16)) return;
       int64_t base;
       if (IS3) base = ((int64_t)(c.c.n * p.hs + ((c.c.th * 16) >> sh_)) * p.ws + ((c.c.tw * (8 * MT)) >> sh_)) * d.x_ld;
       else base = (int64_t)(g0 + c.t) * (BM * MT) * d.x_ld;
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
             for (int j = 0; j < CPR / 2; ++j) {
               const uint32_t a_off = a16 + (IS3 ? sb * 8 + (tap / 3) * PW + (tap % 3) : sb * BM) + 2 * j * (PLANE >> 4);
               const uint32_t b_off = (uint32_t)((tap * CPR + 2 * j) * (LBO_B >> 4));
-              if (!(p.dbg & 2)) tc_mma(tacc + sb * BN, da_base + a_off, db_base + b_off, idesc, (tap > 0 || j > 0) ? 1u : 0u);
+              if (!DBG(2)) tc_mma(tacc + sb * BN, da_base + a_off, db_base + b_off, idesc, (tap > 0 || j > 0) ? 1u : 0u);
             }
           }
         }
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       else if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else asm volatile("cp.async.wait_group 3;" ::: "memory");
       if (pt == 0) TRACE(0, ct.t);
-      if ((affine || relu) && !(p.dbg & 1)) {  // fused prologue, in place on the chunks this thread copied
+      if ((affine || relu) && !DBG(1)) {  // fused prologue, in place on the chunks this thread copied
         if (affine && ct.c.n != ss_n) {
           ss_n = ct.c.n;
           const int64_t si = (d.in_bcast ? 0 : (int64_t)ss_n * d.cin) + cc * 8;
@@ -365,7 +373,6 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       else asm volatile("bar.sync 2, 128;" ::: "memory");
     };
-    const bool has_sb = d.out_scale != nullptr || d.bias != nullptr;
     const bool has_stats = d.stats != nullptr;
     const bool has_res = d.res != nullptr;
     const bool need_px = IS3 || (has_res && d.res_mode != IEA_IN_DIRECT);
@@ -409,6 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
     bf16* const yb = (bf16*)d.y;
     const bf16* const rp = (const bf16*)d.res;
     bool any = false;
+    const int64_t ystep = (int64_t)(IS3 ? 8 : BM) * d.y_ld;
     for (int t = grp; t < my_n; t += 2) {
       const uint32_t ab = t & 3, aph = (t >> 2) & 1;
       int m0, oh = 0, ow0 = 0;
@@ -419,6 +427,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       } else {
         m0 = (g0 + t) * (BM * MT) + et;
       }
+      bf16* const ytile = yb + (int64_t)m0 * d.y_ld;  // sub-tile sb of this thread's pixel: + sb * ystep
       pos_next(p, c);
       pos_next(p, c);
       if (has_stats) {
@@ -456,21 +465,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
 #pragma unroll
           for (int cb = 0; cb < NB; ++cb) {
             const int c0 = cb * 16;
+            // scale / bias applied unconditionally (identity constants when the layer has none): no branch, and
+            // the accumulator words feed the FFMA2 directly
             float2 v[8];
+            if (NB == 1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = make_float2(__uint_as_float(raw[u][cb][2 * j]), __uint_as_float(raw[u][cb][2 * j + 1]));
-            if (has_sb) {
-              if (NB == 1) {
+              for (int j = 0; j < 8; ++j)
+                v[j] = ffma2(make_float2(__uint_as_float(raw[u][cb][2 * j]), __uint_as_float(raw[u][cb][2 * j + 1])), esc[j % NREG], ebs[j % NREG]);
+            } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = ffma2(v[j], esc[j % NREG], ebs[j % NREG]);
-              } else {
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
-                  const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
-                  v[2 * j4] = ffma2(v[2 * j4], make_float2(s4.x, s4.y), make_float2(b4.x, b4.y));
-                  v[2 * j4 + 1] = ffma2(v[2 * j4 + 1], make_float2(s4.z, s4.w), make_float2(b4.z, b4.w));
-                }
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
+                const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
+                v[2 * j4] = ffma2(make_float2(__uint_as_float(raw[u][cb][4 * j4]), __uint_as_float(raw[u][cb][4 * j4 + 1])),
+                                  make_float2(s4.x, s4.y), make_float2(b4.x, b4.y));
+                v[2 * j4 + 1] = ffma2(make_float2(__uint_as_float(raw[u][cb][4 * j4 + 2]), __uint_as_float(raw[u][cb][4 * j4 + 3])),
+                                      make_float2(s4.z, s4.w), make_float2(b4.z, b4.w));
               }
             }
             if (has_res && c0 < d.res_c) {
@@ -501,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
               st_act(d.y, d.y_dtype, (int64_t)m * d.y_ld, v0);
               continue;
             }
-            uint4* yp = reinterpret_cast<uint4*>(yb + (int64_t)m * d.y_ld + c0);
+            uint4* yp = reinterpret_cast<uint4*>(ytile + sb * ystep + c0);
             if (d.acc_c0 >= 0 && c0 >= d.acc_c0) {
               const uint4 r0 = yp[0], r1 = yp[1];
               const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -518,11 +528,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
             uint32_t o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = pack2(v[j].x, v[j].y);
-            if (!(p.dbg & 4)) {
+            if (!DBG(4)) {
               yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
               yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
             }
-            if (has_stats && !(p.dbg & 8)) {
+            if (has_stats && !DBG(8)) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { s1[cb * 8 + j] = fadd2(s1[cb * 8 + j], v[j]); s2[cb * 8 + j] = ffma2(v[j], v[j], s2[cb * 8 + j]); }
             }

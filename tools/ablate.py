@@ -1,6 +1,7 @@
 """Ablation timing of the resident tcgen05 conv kernel (IEA_TC2_DBG bits: 1 no prologue transform,
 2 no MMA issue, 4 no output stores, 8 no statistics, 16 no cp.async loads; IEA_TC2_OCC=2 forces two
-CTAs per SM on the 16-channel variants).  Profiling aid only.
+CTAs per SM on the 16-channel variants).  Profiling aid only: the switches exist in builds made with
+`make -C iea_gan_b200/csrc NVCC="nvcc -DIEA_THIN_DBG"`; the product kernel has them compiled out.
 usage: python tools/ablate.py [dbg[:occ] ...]"""
 import os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
