@@ -583,9 +583,46 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
           ow = (int)(mm - t * (unsigned)d.w); nn = (int)fdiv(t, p.fd_h); oh = (int)(t - (unsigned)nn * (unsigned)d.h);
         }
       }
+      // residual / accumulate operands of a 16-channel block are fetched one block AHEAD of their use (the
+      // first block before the wait for the accumulator): their global-load latency is hidden behind the
+      // TMEM load, the packing and the staging store of the previous block instead of being paid per block
+      const bf16* const rp_ = (const bf16*)d.res;
+      const bool pf_res = valid && d.res != nullptr;
+      const bool pf_acc = valid && d.acc_c0 >= 0;
+      const int res_q = d.res_mode == IEA_IN_POOL2 ? 4 : 1;  // source pixels per output pixel
+      int64_t res_px[4];
+      if (pf_res) {
+        if (d.res_mode == IEA_IN_POOL2) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) res_px[a * 2 + b] = (((int64_t)nn * (2 * d.h) + 2 * oh + a) * (2 * d.w) + 2 * ow + b) * d.res_ld;
+        } else {
+          res_px[0] = d.res_mode == IEA_IN_UP2 ? (((int64_t)nn * (d.h >> 1) + (oh >> 1)) * (d.w >> 1) + (ow >> 1)) * d.res_ld
+                                               : m * d.res_ld;
+        }
+      }
+      uint4 pr[4][2], pa[2];
+      auto prefetch = [&](int cb) {
+        const int c0 = cb * 16;
+        if (pf_res && c0 < d.res_c) {
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4)
+            if (s4 < res_q) {
+              pr[s4][0] = __ldg(reinterpret_cast<const uint4*>(rp_ + res_px[s4] + c0));
+              pr[s4][1] = __ldg(reinterpret_cast<const uint4*>(rp_ + res_px[s4] + c0 + 8));
+            }
+        }
+        if (pf_acc && c0 >= d.acc_c0) {
+          const uint4* yp = reinterpret_cast<const uint4*>((const bf16*)d.y + m * d.y_ld + c0);
+          pa[0] = yp[0]; pa[1] = yp[1];
+        }
+      };
+      prefetch(0);
       mbar_wait(tfull_bar(ab), aph);
       tc_fence_after();
-      for (int cb = 0; cb < p.BN / 16; ++cb) {
+      const int ncb = p.BN / 16;
+      for (int cb = 0; cb < ncb; ++cb) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.BN + cb * 16, v);
         const int c0 = cb * 16;
@@ -598,38 +635,33 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
             v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], s4.z, b4.z); v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], s4.w, b4.w);
           }
           if (d.res && c0 < d.res_c) {
-            const bf16* rp = (const bf16*)d.res;
             float f[16];
             if (d.res_mode == IEA_IN_POOL2) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = 0.f;
-              for (int a = 0; a < 2; ++a)
-                for (int b = 0; b < 2; ++b) {
-                  const bf16* sp = rp + (((int64_t)nn * (2 * d.h) + 2 * oh + a) * (2 * d.w) + 2 * ow + b) * d.res_ld + c0;
-                  float t8[16];
-                  unpack8(*reinterpret_cast<const uint4*>(sp), t8);
-                  unpack8(*reinterpret_cast<const uint4*>(sp + 8), t8 + 8);
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) f[j] += 0.25f * t8[j];
-                }
+              for (int s4 = 0; s4 < 4; ++s4) {
+                float t8[16];
+                unpack8(pr[s4][0], t8);
+                unpack8(pr[s4][1], t8 + 8);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] += 0.25f * t8[j];
+              }
             } else {
-              const bf16* sp = d.res_mode == IEA_IN_UP2
-                                   ? rp + (((int64_t)nn * (d.h >> 1) + (oh >> 1)) * (d.w >> 1) + (ow >> 1)) * d.res_ld + c0
-                                   : rp + m * d.res_ld + c0;
-              unpack8(*reinterpret_cast<const uint4*>(sp), f);
-              unpack8(*reinterpret_cast<const uint4*>(sp + 8), f + 8);
+              unpack8(pr[0][0], f);
+              unpack8(pr[0][1], f + 8);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += f[j];
           }
           if (d.acc_c0 >= 0 && c0 >= d.acc_c0) {
-            const bf16* yp = (const bf16*)d.y + m * d.y_ld + c0;
             float f[16];
-            unpack8(*reinterpret_cast<const uint4*>(yp), f);
-            unpack8(*reinterpret_cast<const uint4*>(yp + 8), f + 8);
+            unpack8(pa[0], f);
+            unpack8(pa[1], f + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += f[j];
           }
+          if (cb + 1 < ncb) prefetch(cb + 1);  // (the operands of this block are consumed: refill for the next one)
           if (d.act == IEA_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);

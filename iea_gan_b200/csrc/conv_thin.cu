@@ -128,7 +128,11 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int CPR, bool IS3, int NB, int MT>
+// EPI: epilogue flavour, fixed at compile time so that each is straight-line code (run-time flags made the
+// compiler shuffle the 16 accumulator registers at every merge point: ~200 instructions per 128x16 block
+// where ~70 do the work).  1: scale/bias + residual read, same-resolution or nearest-up2 [+ statistics]
+// (the GBlock conv4 layers);  2: everything (pooled residual, accumulate, activation, padded 1-channel store)
+template <int CPR, bool IS3, int NB, int MT, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_constant__ Params p) {
   using G = Geo<CPR, IS3, MT>;
   constexpr int PW = G::PW, NCH = G::NCH, NS = G::NS;
@@ -374,7 +378,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       else asm volatile("bar.sync 2, 128;" ::: "memory");
     };
     const bool has_stats = d.stats != nullptr;
-    const bool has_res = d.res != nullptr;
+    const bool has_res = EPI == 1 ? true : (EPI == 2 ? d.res != nullptr : false);
+    const bool res_pool = EPI == 2 && d.res_mode == IEA_IN_POOL2;
+    const bool res_up2 = EPI >= 1 && d.res_mode == IEA_IN_UP2;
     const bool need_px = IS3 || (has_res && d.res_mode != IEA_IN_DIRECT);
     // per-channel scale / bias in registers (smem loads in the tile loop would queue behind the MMA operand reads)
     constexpr int NREG = NB == 1 ? BN / 2 : 1;  // (32 output channels: the registers go to the statistics instead)
@@ -435,6 +441,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
         ev_pos += 2;
         any = true;
       }
+      // residual rows are pulled into L1 one batch of sub-tiles ahead of their use (prefetch: no registers),
+      // so the loads below do not stall every sub-tile on an L2 / HBM round trip
+      const bool res_l1 = !IS3 && has_res && !res_pool;
+      auto res_prefetch = [&](int m) {
+        if (m >= p.M) return;
+        const bf16* sp;
+        if (res_up2) {
+          const unsigned t1 = fdiv((unsigned)m, p.fd_w);
+          const int row = (int)((unsigned)m - t1 * (unsigned)d.w), rn = (int)fdiv(t1, p.fd_h), roh = (int)(t1 - (unsigned)rn * (unsigned)d.h);
+          sp = rp + (((int64_t)rn * (d.h >> 1) + (roh >> 1)) * (d.w >> 1) + (row >> 1)) * d.res_ld;
+        } else {
+          sp = rp + (int64_t)m * d.res_ld;
+        }
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
+      };
+      if (res_l1 && t == grp) {
+#pragma unroll
+        for (int u = 0; u < (NB == 1 ? (MT < 2 ? MT : 2) : 1); ++u) res_prefetch(m0 + u * BM);
+      }
       if (et == 0) TRACE(5, t);
       mbar_wait(tfull0 + 8 * ab, aph);
       tc_fence_after();
@@ -450,6 +475,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
 #pragma unroll
           for (int cb = 0; cb < NB; ++cb)
             tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + ab * (MT * BN) + (sg + u) * BN + cb * 16, raw[u][cb]);
+        if (res_l1) {  // next batch of this macro tile, or the first batch of this group's next macro tile
+#pragma unroll
+          for (int u = 0; u < GRP; ++u) {
+            if (sg + GRP < MT) res_prefetch(m0 + (sg + GRP + u) * BM);
+            else if (t + 2 < my_n) res_prefetch(m0 + 2 * (BM * MT) + u * BM);
+          }
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < GRP; ++u) {
@@ -462,6 +494,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
             const unsigned t1 = fdiv((unsigned)m, p.fd_w);
             row = (int)((unsigned)m - t1 * (unsigned)d.w); rn = (int)fdiv(t1, p.fd_h); roh = (int)(t1 - (unsigned)rn * (unsigned)d.h);
           }
+          const bf16* rsp = nullptr;  // this pixel's residual row (same resolution / nearest-up2 source pixel)
+          if (has_res && !res_pool)
+            rsp = res_up2 ? rp + (((int64_t)rn * (d.h >> 1) + (roh >> 1)) * (d.w >> 1) + (row >> 1)) * d.res_ld
+                          : rp + (int64_t)m * d.res_ld;
 #pragma unroll
           for (int cb = 0; cb < NB; ++cb) {
             const int c0 = cb * 16;
@@ -484,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
               }
             }
             if (has_res && c0 < d.res_c) {
-              if (d.res_mode == IEA_IN_POOL2) {
+              if (res_pool) {
                 const float2 quarter = make_float2(0.25f, 0.25f);
                 for (int a = 0; a < 2; ++a)
                   for (int b = 0; b < 2; ++b) {
@@ -495,16 +531,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
                     for (int j = 0; j < 8; ++j) v[j] = ffma2(bf2_to_f2(w[j]), quarter, v[j]);
                   }
               } else {
-                const bf16* sp = d.res_mode == IEA_IN_UP2
-                                     ? rp + (((int64_t)rn * (d.h >> 1) + (roh >> 1)) * (d.w >> 1) + (row >> 1)) * d.res_ld + c0
-                                     : rp + (int64_t)m * d.res_ld + c0;
-                const uint4 r0 = *reinterpret_cast<const uint4*>(sp), r1 = *reinterpret_cast<const uint4*>(sp + 8);
+                const uint4 r0 = *reinterpret_cast<const uint4*>(rsp + c0), r1 = *reinterpret_cast<const uint4*>(rsp + c0 + 8);
                 const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
               }
             }
-            if (NB == 1 && d.cout == 1) {  // padded output conv: one real channel
+            if (EPI == 2 && NB == 1 && d.cout == 1) {  // padded output conv: one real channel
               float v0 = v[0].x;
               if (d.act == IEA_ACT_RELU) v0 = fmaxf(v0, 0.f);
               else if (d.act == IEA_ACT_TANH) v0 = tanhf(v0);
@@ -512,16 +545,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
               continue;
             }
             uint4* yp = reinterpret_cast<uint4*>(ytile + sb * ystep + c0);
-            if (d.acc_c0 >= 0 && c0 >= d.acc_c0) {
+            if (EPI == 2 && d.acc_c0 >= 0 && c0 >= d.acc_c0) {
               const uint4 r0 = yp[0], r1 = yp[1];
               const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
             }
-            if (d.act == IEA_ACT_RELU) {
+            if (EPI == 2 && d.act == IEA_ACT_RELU) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); }
-            } else if (d.act == IEA_ACT_TANH) {
+            } else if (EPI == 2 && d.act == IEA_ACT_TANH) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { v[j].x = tanhf(v[j].x); v[j].y = tanhf(v[j].y); }
             }
@@ -646,10 +679,18 @@ static int thin_launch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
   int rc = thin_prepare<CPR, IS3, MT>(d, p, grid, smem);
   if (rc) return rc;
   if (grid_only) { *grid_only = grid; return 0; }
-  auto kern = thin::conv_thin_kernel<CPR, IS3, NB, MT>;
-  IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, thin::THREADS, smem, s>>>(p);
-  return check_launch("iea_conv_fprop(tcgen05 thin)");
+  auto run = [&](auto kern) -> int {
+    IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, thin::THREADS, smem, s>>>(p);
+    return check_launch("iea_conv_fprop(tcgen05 thin)");
+  };
+  // (a compile-time "plain" flavour measured no faster than the generic one -- without a residual the
+  //  producers, not the epilogue, pace these kernels -- so only the residual flavour is specialised)
+  const bool simple = d->acc_c0 < 0 && d->act == IEA_ACT_NONE && d->cout != 1;
+  if constexpr (!IS3) {
+    if (simple && d->res && d->res_mode != IEA_IN_POOL2) return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 1>);
+  }
+  return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 2>);
 }
 
 static int thin_dispatch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
