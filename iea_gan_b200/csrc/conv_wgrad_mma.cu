@@ -45,7 +45,7 @@ struct Params {
   float* gpart;
   float* cs_parts;  // [gridDim.x][cout] column sums of g (bias gradient) or NULL
   int64_t M;
-  int n_tiles, tiles_w, tiles_h, hs, ws, cpa, cpg, cin_eff, cout_eff, stages, depth, P, WP;
+  int n_tiles, tiles_w, tiles_h, hs, ws, cpa, cpg, cpa_sh, cpg_sh, cin_eff, cout_eff, stages, depth, P, WP;
   int nib_l, ncb_l, gi;  // output split over blockIdx.y: ci blocks / co blocks per CTA, groups along ci
   uint32_t plane_a, plane_g, stage_bytes, g_off;
 };
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
     const uint32_t s0 = sbase + (uint32_t)(it % p.stages) * p.stage_bytes;
     // ---- input patch (raw; transformed in place after it landed)
     for (int e = tid; e < total_a; e += 256) {
-      const int pp = e / p.cpa, c = e - pp * p.cpa;
+      const int pp = e >> p.cpa_sh, c = e & (p.cpa - 1);  // (cpa, cpg are powers of two)
       int ih = 0, iw = 0; int64_t m = 0;
       const bool in = pix_a(o, pp, ih, iw, m);
       const uint32_t dst = s0 + c * p.plane_a + pp * 16;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
     }
     // ---- output-gradient tile: 128 pixels x cout, pixel r = (r>>3, r&7) inside a 16x8 tile
     for (int e = tid; e < total_g; e += 256) {
-      const int r = e / p.cpg, c = e - r * p.cpg;
+      const int r = e >> p.cpg_sh, c = e & (p.cpg - 1);
       int64_t m;
       bool in = true;
       if (IS3) {  // (images smaller than / not a multiple of the 16x8 tile: rows and columns beyond the edge are zero)
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
   if (p.P <= 8) { pair0 = warp % p.P; kg = warp / p.P; } else { pair0 = warp * NPAIR; }
   float sc[8], sh[8];
   int ss_n = -1;
-  const int my_c = tid % p.cpa;  // 256 % cpa == 0: the chunk column of this thread is fixed
+  const int my_c = tid & (p.cpa - 1);  // 256 % cpa == 0: the chunk column of this thread is fixed
 
   for (int it = 0; it < my_tiles; ++it) {
     if (it + D - 1 < my_tiles) issue(it + D - 1);
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
         ss_n = o.n;
       }
       for (int e = tid; e < total_a; e += 256) {
-        const int pp = e / p.cpa;
+        const int pp = e >> p.cpa_sh;
         int ih = 0, iw = 0; int64_t m = 0;
         if (!pix_a(o, pp, ih, iw, m)) continue;
         uint4* q = reinterpret_cast<uint4*>(sp + my_c * p.plane_a + pp * 16);
@@ -376,6 +376,8 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   p->fd_tw = wg::make_fastdiv(p->tiles_w); p->fd_th = wg::make_fastdiv(p->tiles_h);
   p->fd_hw = wg::make_fastdiv(d->h * d->w);
   p->cpa = nib_l * 2; p->cpg = ncb_l * 2; p->cin_eff = cin_eff; p->cout_eff = cout_eff;
+  p->cpa_sh = 0; while ((1 << p->cpa_sh) < p->cpa) ++p->cpa_sh;
+  p->cpg_sh = 0; while ((1 << p->cpg_sh) < p->cpg) ++p->cpg_sh;
   p->nib_l = nib_l; p->ncb_l = ncb_l; p->gi = nib / nib_l;
   p->plane_a = plane_a;
   p->plane_g = plane_g;
