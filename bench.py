@@ -45,7 +45,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples during the timed region: NVML every 20 ms (nvidia-smi, 5 Hz,
+    when NVML is not importable)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -53,30 +54,66 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.mx, self.reasons, self.stop_flag = index, [], [], set(), False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map the (possibly CUDA_VISIBLE_DEVICES-remapped) ordinal by PCI bus id
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        h = hi
+            self.nv, self.h = pynvml, h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def _nvml(self):
+        nv, h = self.nv, self.h
+        self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        self.mx.append(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [t.strip() for t in line.split(",")]
+            if r[1].isdigit():
+                self.sm.append(int(r[1]))
+            if r[2].isdigit():
+                self.mx.append(int(r[2]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([t.strip() for t in line.split(",")])
+                if self.nv is not None:
+                    self._nvml()
+                else:
+                    self._smi()
             except Exception:
-                pass
-            time.sleep(0.2)
+                if self.nv is not None:
+                    self.nv = None  # fall back to nvidia-smi
+            time.sleep(0.02 if self.nv is not None else 0.2)
 
     def summary(self):
         self.stop_flag = True
-        sm = sorted(int(r[1]) for r in self.rows if r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if r[2].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def timed(fn, steps, warmup, dist_on):
@@ -141,10 +178,18 @@ def top_kernel_roofline(E_, events, hbm_peak, which):
     esz = 2 if E_.act_dtype() == torch.bfloat16 else 4
     bytes_ = 2 * n * h * w * c * esz + 9 * c * c * esz
     ach = bytes_ / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "iea_conv_fprop 16->16 3x3 @256x256 (+BN/ReLU prologue, stats epilogue)",
+    traffic, traffic_src = None, None  # DRAM bytes of this launch from the committed `ncu --set full` capture
+    tp = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+    if os.path.exists(tp) and events == 4:
+        with open(tp) as f:
+            t = json.load(f)
+        traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+    return {"bound": "hbm", "kernel": "iea_conv_fprop 16->16 3x3 @256x256 (+BN/ReLU prologue, stats epilogue), "
+                                      "thin::conv_thin_kernel<2,1,1,4>, %d images" % n,
             "achieved": round(ach, 1), "peak": hbm_peak, "peak_source": which, "unit": "GB/s",
-            "frac": round(ach / hbm_peak, 4), "traffic": None, "ms_per_launch": round(ms, 4),
-            "algorithmic_bytes_per_launch": bytes_, "impl": os.environ.get("IEA_CONV_IMPL", "auto")}
+            "frac": round(ach / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+            "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": bytes_,
+            "impl": os.environ.get("IEA_CONV_IMPL", "auto")}
 
 
 def cpu_oracle_sample(cfg, reps):
