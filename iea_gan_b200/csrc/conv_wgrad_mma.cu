@@ -15,6 +15,7 @@
 // m16n8k16 shape matches the 16-channel blocks exactly, ldmatrix takes per-lane row addresses (so the
 // shifted tap views are free) and each g fragment is reused by all 9 taps: ~40 KB of smem reads/tile.
 #include "tc_common.cuh"
+#include <stdlib.h>
 using namespace iea;
 
 namespace wg {
@@ -323,6 +324,231 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Macro-tile variant for the thin 3x3 layers at high resolution (Cin, Cout in {16, 32}; same-resolution or
+// nearest-up2 input): one pipeline item is MT side-by-side 16x8 tiles -- an 18 x (8*MT+2) halo patch of x and
+// 128*MT rows of g -- so the two block barriers, the tile bookkeeping and the halo re-reads are paid once per
+// 128*MT pixels, and every thread owns the same chunk slots of every patch: global / shared offsets of its
+// cp.async copies are computed once per kernel (no divisions or coordinate tests in the tile loop), the fused
+// BN-affine + ReLU prologue is one LDS / 4 packed-bf16 FMA / STS per chunk (the same rounding as the forward
+// kernel, conv_thin.cu), border patches use per-slot side masks.
+struct P3 {
+  iea_conv_desc d;
+  const bf16* g; int g_ld;
+  float* gpart; float* cs_parts;
+  int n_macro, mtw, mth, hs, ws, stages, depth;
+  FastDiv fd_mtw, fd_mth;
+};
+
+template <int CPA, int CPG, int MT>
+struct G3 {
+  static constexpr int PWM = 8 * MT + 2;
+  static constexpr int NPA = PH * PWM;                 // patch pixels
+  static constexpr int NPG = 128 * MT;                 // g rows
+  static constexpr int NSA = (NPA * CPA + 255) / 256;  // chunk slots per thread
+  static constexpr int NSG = NPG * CPG / 256;
+  static constexpr uint32_t PLA = (NPA * 16 + 127) / 128 * 128 + 128 / CPA;
+  static constexpr uint32_t PLG = NPG * 16 + 128 / CPG;
+  static constexpr uint32_t GOFF = CPA * PLA;
+  static constexpr uint32_t STAGE = (GOFF + CPG * PLG + 127) / 128 * 128;
+};
+
+template <int CPA, int CPG, int MT>
+__global__ void __launch_bounds__(256) wgrad3_kernel(const P3 p) {
+  using G = G3<CPA, CPG, MT>;
+  constexpr int PWM = G::PWM, NSA = G::NSA, NSG = G::NSG;
+  constexpr int NIB = CPA / 2, NCB = CPG / 2, P = NIB * NCB, WP = 8 / P, KS = 8 * MT;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const iea_conv_desc& d = p.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const int my_n = (int)blockIdx.x < p.n_macro ? (p.n_macro - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const bool affine = d.in_scale != nullptr, relu = d.in_relu != 0;
+  const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
+  const int D = p.depth;
+
+  // ---- slot tables (tile independent)
+  const int ca = tid % CPA, cg = tid % CPG;
+  int goa[NSA], gog[NSG];
+  uint32_t soa[NSA], sog[NSG];
+  uint32_t m_top = 0, m_bot = 0, m_left = 0, m_right = 0, m_valid = 0;
+#pragma unroll
+  for (int i = 0; i < NSA; ++i) {
+    const int q = tid + 256 * i, pp = q / CPA;
+    if (q < G::NPA * CPA) m_valid |= 1u << i;
+    const int pi = pp / PWM, pj = pp - pi * PWM;
+    goa[i] = (((pi - 1) >> sh_) * p.ws + ((pj - 1) >> sh_)) * d.x_ld + ca * 8;
+    soa[i] = ca * G::PLA + pp * 16;
+    if (pi == 0) m_top |= 1u << i;
+    if (pi == PH - 1) m_bot |= 1u << i;
+    if (pj == 0) m_left |= 1u << i;
+    if (pj == PWM - 1) m_right |= 1u << i;
+  }
+#pragma unroll
+  for (int i = 0; i < NSG; ++i) {
+    const int q = tid + 256 * i, r = q / CPG;            // r = sb*128 + (row*8 + col) inside the sub-tile
+    const int sb = r >> 7, lr = r & 127;
+    gog[i] = ((lr >> 3) * d.w + sb * 8 + (lr & 7)) * p.g_ld + cg * 8;
+    sog[i] = G::GOFF + cg * G::PLG + r * 16;
+  }
+  struct Pos { int n, th, tw; };
+  auto pos_of = [&](int item) {
+    Pos c;
+    const unsigned t = fdiv((unsigned)item, p.fd_mtw);
+    c.tw = (int)((unsigned)item - t * (unsigned)p.mtw);
+    c.n = (int)fdiv(t, p.fd_mth);
+    c.th = (int)(t - (unsigned)c.n * (unsigned)p.mth);
+    return c;
+  };
+  auto pad_of = [&](const Pos& c) -> uint32_t {
+    return (c.th == 0 ? m_top : 0u) | (c.th == p.mth - 1 ? m_bot : 0u) | (c.tw == 0 ? m_left : 0u) |
+           (c.tw == p.mtw - 1 ? m_right : 0u);
+  };
+  const bf16* xb = (const bf16*)d.x;
+  auto issue = [&](int it) {
+    const Pos c = pos_of((int)blockIdx.x + it * (int)gridDim.x);
+    const uint32_t s0 = sbase + (uint32_t)(it % p.stages) * G::STAGE;
+    const bf16* ap = xb + ((int64_t)(c.n * p.hs + ((c.th * 16) >> sh_)) * p.ws + ((c.tw * (8 * MT)) >> sh_)) * d.x_ld;
+    const bf16* gp = p.g + ((int64_t)(c.n * d.h + c.th * 16) * d.w + c.tw * (8 * MT)) * p.g_ld;
+    const uint32_t pad = pad_of(c);
+#pragma unroll
+    for (int i = 0; i < NSA; ++i) {
+      if (!(m_valid >> i & 1)) continue;
+      if (pad >> i & 1) asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(s0 + soa[i]), "r"(0) : "memory");
+      else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + soa[i]), "l"(ap + goa[i]) : "memory");
+    }
+#pragma unroll
+    for (int i = 0; i < NSG; ++i)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + sog[i]), "l"(gp + gog[i]) : "memory");
+  };
+
+  const int pair = warp % P, kg = warp / P;
+  const int cb = pair / NIB, ib = pair - cb * NIB;
+  const bool cs_on = p.cs_parts != nullptr && ib == 0;
+  float acc[9][2][4], acc_cs[4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[t][j][r] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) acc_cs[r] = 0.f;
+
+  for (int k = 0; k < D - 1; ++k) {
+    if (k < my_n) issue(k);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __nv_bfloat162 sc2[4], sh2[4];
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+  int ss_n = -1;
+  const int mat = lane >> 3, rr = lane & 7;
+  for (int it = 0; it < my_n; ++it) {
+    if (it + D - 1 < my_n) issue(it + D - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 2;" ::: "memory");
+    const uint32_t s0 = sbase + (uint32_t)(it % p.stages) * G::STAGE;
+    if (affine || relu) {  // fused prologue, in place on the chunks this thread copied; padding stays zero
+      const Pos c = pos_of((int)blockIdx.x + it * (int)gridDim.x);
+      if (affine && c.n != ss_n) {
+        ss_n = c.n;
+        const int64_t si = (d.in_bcast ? 0 : (int64_t)ss_n * d.cin) + ca * 8;
+        const float4 a0 = *reinterpret_cast<const float4*>(d.in_scale + si), a1 = *reinterpret_cast<const float4*>(d.in_scale + si + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(d.in_shift + si), b1 = *reinterpret_cast<const float4*>(d.in_shift + si + 4);
+        sc2[0] = __floats2bfloat162_rn(a0.x, a0.y); sc2[1] = __floats2bfloat162_rn(a0.z, a0.w);
+        sc2[2] = __floats2bfloat162_rn(a1.x, a1.y); sc2[3] = __floats2bfloat162_rn(a1.z, a1.w);
+        sh2[0] = __floats2bfloat162_rn(b0.x, b0.y); sh2[1] = __floats2bfloat162_rn(b0.z, b0.w);
+        sh2[2] = __floats2bfloat162_rn(b1.x, b1.y); sh2[3] = __floats2bfloat162_rn(b1.z, b1.w);
+      }
+      const uint32_t live = m_valid & ~pad_of(c);
+      uint8_t* a = smem + (size_t)(it % p.stages) * G::STAGE;
+#pragma unroll
+      for (int i = 0; i < NSA; ++i) {
+        if (!(live >> i & 1)) continue;
+        uint4* q = reinterpret_cast<uint4*>(a + soa[i]);
+        uint4 v = *q;
+        __nv_bfloat162* x2 = reinterpret_cast<__nv_bfloat162*>(&v);
+        if (affine && relu) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x2[j] = __hfma2_relu(x2[j], sc2[j], sh2[j]);
+        } else if (affine) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x2[j] = __hfma2(x2[j], sc2[j], sh2[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x2[j] = __hmax2(x2[j], zero2);
+        }
+        *q = v;
+      }
+    }
+    __syncthreads();
+    // ---- tensor-core accumulation: this warp's (co block, ci block) pair over its share of the k-steps
+    for (int ks = kg; ks < KS; ks += WP) {
+      const int sb = ks >> 3, kl = ks & 7;
+      uint32_t a[4];
+      ldsm_x4_t(s0 + G::GOFF + (cb * 2 + (mat & 1)) * G::PLG + (sb * 128 + kl * 16 + (mat >> 1) * 8 + rr) * 16, a[0], a[1], a[2], a[3]);
+      if (cs_on) mma16816(acc_cs, a, 0x3F803F80u, 0x3F803F80u);
+      const uint32_t brow = s0 + (ib * 2 + (mat >> 1)) * G::PLA + (uint32_t)((2 * kl + (mat & 1)) * PWM + sb * 8 + rr) * 16;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(brow + (uint32_t)((t / 3) * PWM + t % 3) * 16, b0, b1, b2, b3);
+        mma16816(acc[t][0], a, b0, b1);
+        mma16816(acc[t][1], a, b2, b3);
+      }
+    }
+    __syncthreads();  // the stage is overwritten by the cp.async of the next iteration
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // ---- fold the k-step groups (fixed order), then one partial per CTA: gpart[blockIdx.x][cout][9][cin]
+  if (WP > 1) {
+    float* scr = reinterpret_cast<float*>(smem);  // [P][76][32]
+    __syncthreads();
+    for (int kgi = 1; kgi < WP; ++kgi) {
+      if (kg == kgi) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) scr[(pair * 76 + t * 8 + j * 4 + r) * 32 + lane] = acc[t][j][r];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) scr[(pair * 76 + 72 + r) * 32 + lane] = acc_cs[r];
+      }
+      __syncthreads();
+      if (kg == 0) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[t][j][r] += scr[(pair * 76 + t * 8 + j * 4 + r) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc_cs[r] += scr[(pair * 76 + 72 + r) * 32 + lane];
+      }
+      __syncthreads();
+    }
+  }
+  if (kg != 0) return;
+  float* out = p.gpart + (int64_t)blockIdx.x * d.cout * 9 * d.cin;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int co = cb * 16 + (lane >> 2) + (r >= 2 ? 8 : 0);
+        const int ci = ib * 16 + j * 8 + 2 * (lane & 3) + (r & 1);
+        out[((int64_t)co * 9 + t) * d.cin + ci] = acc[t][j][r];
+      }
+  if (cs_on && (lane & 3) == 0) {
+    const int co = cb * 16 + (lane >> 2);
+    p.cs_parts[(int64_t)blockIdx.x * d.cout + co] = acc_cs[0];
+    p.cs_parts[(int64_t)blockIdx.x * d.cout + co + 8] = acc_cs[2];
+  }
+}
+
 // sum of the per-CTA partials in a fixed order: out[i] = sum_s gpart[s][i]
 __global__ void wgrad_reduce_kernel(const float* gpart, int nsplit, int64_t total, float* out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -396,8 +622,69 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
 int iea_conv_c1_wgrad_grid(const iea_conv_desc* d, int g_dtype, int g_ld);
 int iea_conv_c1_wgrad(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* parts, cudaStream_t s);
 
+// macro-tile kernel: 0 = shape not handled, else MT (sub-tiles per macro tile)
+static int wgrad3_mt(const iea_conv_desc* d, int g_dtype, int g_ld) {
+  { const char* e_ = getenv("IEA_WGRAD3"); if (e_ && e_[0] == '0') return 0; }  // test / profiling switch: generic mma kernel
+  if (d->ksize != 3 || (d->cin != 16 && d->cin != 32) || (d->cout != 16 && d->cout != 32)) return 0;
+  if (d->in_mode == IEA_IN_POOL2 || d->x_dtype != IEA_BF16 || g_dtype != IEA_BF16) return 0;
+  if (d->x_ld % 8 || g_ld % 8 || (reinterpret_cast<uintptr_t>(d->x) & 15)) return 0;
+  if (d->h % 16 || d->w % 16) return 0;
+  if (d->in_scale && ((reinterpret_cast<uintptr_t>(d->in_scale) & 15) || (reinterpret_cast<uintptr_t>(d->in_shift) & 15))) return 0;
+  const int64_t M = d->n * (int64_t)d->h * d->w;
+  if (M >= (1ll << 31) || M * (int64_t)(d->x_ld > g_ld ? d->x_ld : g_ld) >= (1ll << 31) || M < 8192) return 0;
+  int mt = (d->cin == 16 && d->cout == 16) ? 4 : 2;
+  while (mt > 1 && d->w % (8 * mt)) mt >>= 1;
+  return mt >= 2 ? mt : 0;
+}
+template <int CPA, int CPG, int MT>
+static int wgrad3_setup(const iea_conv_desc* d, wg::P3& p, int& grid, uint32_t& smem) {
+  using G = wg::G3<CPA, CPG, MT>;
+  p.d = *d;
+  p.hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : d->h;
+  p.ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : d->w;
+  p.mtw = d->w / (8 * MT); p.mth = d->h / 16;
+  p.n_macro = (int)(d->n * (int64_t)p.mtw * p.mth);
+  p.fd_mtw = wg::make_fastdiv(p.mtw); p.fd_mth = wg::make_fastdiv(p.mth);
+  p.stages = 3; p.depth = 3;
+  if (p.stages * G::STAGE > 110 * 1024) { p.stages = 2; p.depth = 2; }
+  smem = p.stages * G::STAGE;
+  constexpr uint32_t fold = (uint32_t)((CPA / 2) * (CPG / 2)) * 76 * 32 * 4;
+  if (smem < fold) smem = fold;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int occ = smem <= 110 * 1024 ? 2 : 1;
+  grid = p.n_macro < sms * occ ? p.n_macro : sms * occ;
+  return 0;
+}
+// grid of the macro-tile launch (0: not handled); launches when parts != nullptr
+static int wgrad3_run(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* parts, float* cs_parts, cudaStream_t s) {
+  const int mt = wgrad3_mt(d, g_dtype, g_ld);
+  if (!mt) return 0;
+  wg::P3 p; int grid = 0; uint32_t smem = 0;
+  const int cpa = d->cin / 8, cpg = d->cout / 8;
+  p.g = (const bf16*)g; p.g_ld = g_ld; p.gpart = parts; p.cs_parts = cs_parts;
+#define IEA_W3(A_, G_, M_)                                                                                      \
+  if (cpa == A_ && cpg == G_ && mt == M_) {                                                                       \
+    wgrad3_setup<A_, G_, M_>(d, p, grid, smem);                                                                    \
+    if (parts) {                                                                                                  \
+      auto kern = wg::wgrad3_kernel<A_, G_, M_>;                                                                   \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1; \
+      kern<<<grid, 256, smem, s>>>(p);                                                                            \
+    }                                                                                                             \
+    return grid;                                                                                                  \
+  }
+  IEA_W3(2, 2, 4) IEA_W3(2, 2, 2) IEA_W3(2, 4, 2) IEA_W3(4, 2, 2) IEA_W3(4, 4, 2)
+#undef IEA_W3
+  return 0;
+}
+
 extern "C" int iea_conv_wgrad_mma_slices(const iea_conv_desc* d, int g_dtype, int g_ld) {
   if (const int c1g = iea_conv_c1_wgrad_grid(d, g_dtype, g_ld)) return c1g + 1;  // 1-channel side: conv_c1.cu
+  if (const int g3 = wgrad3_run(d, nullptr, g_dtype, g_ld, nullptr, nullptr, nullptr)) {
+    const int64_t total = (int64_t)d->cout * 9 * d->cin;
+    return g3 + 1 + (int)(((int64_t)g3 * d->cout + total - 1) / total);
+  }
   wg::Params p; int npair;
   if (!wgrad_mma_plan(d, g_dtype, g_ld, &p, &npair)) return 0;
   int dev = 0, sms = 148;
@@ -420,6 +707,18 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
     int rb = (int)((total + 255) / 256);
     wg::wgrad_reduce_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>(gpart + total, c1g, total, gpart);
     return check_launch("iea_conv_wgrad_mma(1-channel)");  // 0: the bias gradient was not produced
+  }
+  if (const int g3 = wgrad3_run(d, nullptr, g_dtype, g_ld, nullptr, nullptr, nullptr)) {  // macro-tile kernel
+    const int64_t total = (int64_t)d->cout * 9 * d->cin;
+    float* parts = gpart + total;
+    float* csp = dbias ? gpart + (int64_t)(g3 + 1) * total : nullptr;
+    const int rc3 = wgrad3_run(d, g, g_dtype, g_ld, parts, csp, (cudaStream_t)stream);
+    IEA_CHECK_ARG(rc3 == g3, "iea_conv_wgrad_mma(macro tile): launch set-up failed");
+    int rb = (int)((total + 255) / 256);
+    wg::wgrad_reduce_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>(parts, g3, total, gpart);
+    if (dbias) wg::wgrad_reduce_kernel<<<(d->cout + 255) / 256, 256, 0, (cudaStream_t)stream>>>(csp, g3, d->cout, dbias);
+    const int rc = check_launch("iea_conv_wgrad_mma(macro tile)");
+    return rc ? rc : (dbias ? 1 : 0);
   }
   wg::Params p; int npair;
   IEA_CHECK_ARG(wgrad_mma_plan(d, g_dtype, g_ld, &p, &npair), "iea_conv_wgrad_mma: shape not handled (cin=%d cout=%d k=%d)",

@@ -315,7 +315,10 @@ def _tc_vs_generic(eng, variant, cin, cout, k, mode, relu, aff, resm, hw, n):
                                               (128, 128, 3, (16, 16), "bf16"), (512, 128, 1, (8, 8), "bf16"),
                                               (128, 512, 1, (8, 8), "bf16"), (256, 64, 1, (16, 16), "bf16"),
                                               (128, 128, 3, (8, 8), "bf16"), (128, 128, 3, (4, 4), "bf16"),
-                                              (32, 16, 3, (12, 20), "bf16")])
+                                              (32, 16, 3, (12, 20), "bf16"),
+                                              # macro-tile kernel (Cin, Cout in {16, 32}; 4- and 2-wide macro tiles)
+                                              (16, 16, 3, (32, 64), "bf16"), (32, 32, 3, (16, 32), "bf16"),
+                                              (16, 32, 3, (32, 16), "bf16"), (32, 16, 3, (16, 16), "bf16")])
 def test_wgrad_mma_thin_and_wide(eng, cin, cout, k, hw, gdt):
     """The 1-channel stem / output convs (zero-extended operands) and the many-block 1x1 shapes of the
     tensor-core weight-gradient kernel against the CUDA-core kernel."""
