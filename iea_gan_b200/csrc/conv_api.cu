@@ -14,6 +14,8 @@ int iea_conv_fprop_thin(const iea_conv_desc* d, cudaStream_t s);
 int iea_conv_thin_stats_slots(const iea_conv_desc* d);
 int iea_conv_c1_fwd_ok(const iea_conv_desc* d);
 int iea_conv_c1_fwd(const iea_conv_desc* d, cudaStream_t s);
+int iea_linear_skinny_ok(const iea_conv_desc* d);
+int iea_linear_skinny(const iea_conv_desc* d, cudaStream_t s);
 
 // tcgen05 variant selection: resident-weights/patch kernel when it applies, else the streaming one.
 // IEA_TC_VARIANT=stream forces the streaming kernel (used by the tests to cover both).
@@ -59,6 +61,7 @@ extern "C" int iea_conv_fprop(const iea_conv_desc* d, iea_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (d->impl == IEA_IMPL_GENERIC) return iea_conv_fprop_generic(d, s);
   if (d->impl == IEA_IMPL_AUTO && iea_conv_c1_fwd_ok(d)) return iea_conv_c1_fwd(d, s);  // 1-channel input: CUDA cores
+  if (d->impl == IEA_IMPL_AUTO && iea_linear_skinny_ok(d)) return iea_linear_skinny(d, s);  // few rows, long K: cluster split-K
   if (d->impl == IEA_IMPL_TCGEN05) {
     IEA_CHECK_ARG(iea_conv_tc_ok(d) || iea_conv_tc2_ok(d), "iea_conv_fprop: tcgen05 path requested for an unsupported shape "
                   "(cin=%d cout=%d k=%d)", d->cin, d->cout, d->ksize);

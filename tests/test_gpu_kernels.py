@@ -383,3 +383,38 @@ def test_attention_tcgen05_vs_torch(eng, n, hw, hwk):
     for name, got, ref, gen in zip(("o", "dtheta", "dphi", "dg"), outs["tcgen05"], refs, outs["generic"]):
         assert rel(got, ref) < 1.5e-2, name
         assert rel(got, gen) < 1.5e-2, name
+
+
+@pytest.mark.parametrize("rows,cin,cout,xdt,aff,relu,res", [
+    (320, 12096, 256, "fp32", True, False, False),   # grouped ccbn data gradient: cluster of 8 over K
+    (80, 256, 8192, "fp32", False, False, False),    # G.linear forward: one K slice, many column tiles
+    (120, 1536, 512, "bf16", False, True, True),     # ragged rows, bf16 input, fused ReLU + residual
+    (40, 516, 260, "fp32", True, True, False)])      # K and N tails
+def test_skinny_linear_cluster_splitk(eng, rows, cin, cout, xdt, aff, relu, res):
+    """linear_skinny.cu (64x64 tiles, split-K over a thread-block cluster reduced through distributed
+    shared memory) against torch fp32: y = relu?(x*s+t) W^T / sigma + b (+ residual)."""
+    from iea_gan_b200 import _lib as L
+    dev = "cuda"
+    torch.manual_seed(13)
+    x = torch.randn(rows, cin, device=dev)
+    x = x.bfloat16() if xdt == "bf16" else x
+    w = torch.randn(cout, cin, device=dev) * 0.05
+    b = torch.randn(cout, device=dev)
+    osc = torch.tensor([0.7], device=dev)
+    sc = torch.rand(cin, device=dev) + 0.5 if aff else None
+    sh = torch.randn(cin, device=dev) if aff else None
+    r = torch.randn(rows, cout, device=dev) if res else None
+    y = torch.empty(rows, cout, device=dev)
+    d = eng._desc(rows, 1, 1, cin, cout, 1, x, x.data_ptr(), cin, 0, relu, sc, sh, w, osc, 0, b,
+                  eng.Var(r) if res else None, 0, cout if res else 0, -1, y, y.data_ptr(), cout, 0, None, in_bcast=1 if aff else 0)
+    L.call("iea_conv_fprop", C.byref(d), L.stream())
+    t = x.float()
+    if aff:
+        t = t * sc + sh
+    if relu:
+        t = t.relu()
+    ref = (t.double() @ w.double().t()).float() * 0.7 + b
+    if res:
+        ref = ref + r
+    torch.cuda.synchronize()
+    assert rel(y, ref) < 2e-5
