@@ -173,6 +173,87 @@ __global__ void affine_act_kernel(const void* x, int x_dtype, const float* scale
   }
 }
 
+// training-mode finalize in ONE launch: grid (events, ceil(c/8)) blocks reduce the tile partials of their
+// (event, 8 channels) in double exactly like bn_reduce_kernel; the LAST block to finish for a channel group
+// (ticket counter) then does everything that needs all events of those channels: running-statistics update in
+// event order, variance -> rstd, and the per-image scale / shift the consumer convolution's prologue reads.
+// Fixed summation orders throughout: deterministic, whichever block ends up last.
+__device__ unsigned int g_bn_ticket[1024];  // self-resetting; one entry per 8-channel group
+__global__ void __launch_bounds__(256) bn_finalize_fused_kernel(const float* partials, int tiles, double count, int events,
+                                                                int imgs, int c, const float* gain, int64_t gain_ld,
+                                                                float gain_add, const float* bias, int64_t bias_ld,
+                                                                float* stored_mean, float* stored_var, float momentum,
+                                                                float eps, float* mean_io, float* rstd_io, float* scale,
+                                                                float* shift) {
+  __shared__ double r1[256], r2[256];
+  __shared__ bool last;
+  const int e = blockIdx.x, cl = threadIdx.x & 7, tl = threadIdx.x >> 3, cc = blockIdx.y * 8 + cl;
+  double s1 = 0.0, s2 = 0.0;
+  if (cc < c) {
+    const float* p = partials + ((int64_t)e * tiles * c + cc) * 2;
+    for (int t = tl; t < tiles; t += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(p + (int64_t)t * c * 2);
+      s1 += (double)v.x; s2 += (double)v.y;
+    }
+  }
+  r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+  __syncthreads();
+  if (tl == 0 && cc < c) {
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < 32; ++l) { a += r1[l * 8 + cl]; b += r2[l * 8 + cl]; }
+    const double m = a / count;
+    double var = b / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean_io[e * c + cc] = (float)m;
+    rstd_io[e * c + cc] = (float)var;  // variance until the last block converts it
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&g_bn_ticket[blockIdx.y], 1u);
+    last = t == (unsigned int)events - 1;
+    if (last) g_bn_ticket[blockIdx.y] = 0;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float* rs_s = reinterpret_cast<float*>(r1);  // [events][8] rstd of this channel group (events <= 64)
+  if (tl == 0 && cc < c) {
+    float rm = stored_mean ? stored_mean[cc] : 0.f, rv = stored_var ? stored_var[cc] : 1.f;
+    for (int ev = 0; ev < events; ++ev) {
+      const double var = (double)__ldcg(rstd_io + ev * c + cc);
+      const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+      rm = (1.f - momentum) * rm + momentum * __ldcg(mean_io + ev * c + cc);
+      rv = (1.f - momentum) * rv + momentum * (float)unb;
+    }
+    if (stored_mean) { stored_mean[cc] = rm; stored_var[cc] = rv; }
+  }
+  for (int i = threadIdx.x; i < events * 8; i += 256) {
+    const int ev = i >> 3, ch = blockIdx.y * 8 + (i & 7);
+    if (ch < c) {
+      const float rstd = (float)(1.0 / sqrt((double)__ldcg(rstd_io + ev * c + ch) + (double)eps));
+      if (ev < 64) rs_s[ev * 8 + (i & 7)] = rstd;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < events * 8; i += 256) {
+    const int ev = i >> 3, ch = blockIdx.y * 8 + (i & 7);
+    if (ch < c) rstd_io[ev * c + ch] = rs_s[ev * 8 + (i & 7)];
+  }
+  const int64_t nimg = (int64_t)events * imgs;
+  for (int64_t i = threadIdx.x; i < nimg * 8; i += 256) {
+    const int64_t n = i >> 3;
+    const int ch = blockIdx.y * 8 + (int)(i & 7);
+    if (ch >= c) continue;
+    const int ev = (int)(n / imgs);
+    const float rstd = rs_s[ev * 8 + (i & 7)], mean = __ldcg(mean_io + ev * c + ch);
+    const float gn = gain_add + (gain ? gain[n * gain_ld + ch] : 0.f);
+    const float bs = bias ? bias[n * bias_ld + ch] : 0.f;
+    const float sc = rstd * gn;
+    scale[n * c + ch] = sc;
+    shift[n * c + ch] = bs - mean * sc;
+  }
+}
 }  // namespace
 
 extern "C" int iea_bn_stats(const void* x, int x_dtype, int x_ld, int64_t rows, int rows_per_event, int c,
@@ -195,6 +276,12 @@ extern "C" int iea_bn_finalize(const float* partials, int events, int tiles_per_
                                float* scale, float* shift, iea_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)events * imgs_per_event;
+  if (training && events <= 64 && c <= 8 * 1024) {
+    bn_finalize_fused_kernel<<<dim3(events, cdiv(c, 8)), 256, 0, st>>>(
+        partials, tiles_per_event, (double)count_per_event, events, imgs_per_event, c, gain, gain_ld, gain_add, bias, bias_ld,
+        stored_mean, stored_var, momentum, eps, mean_out, rstd_out, scale, shift);
+    return check_launch("iea_bn_finalize(fused)");
+  }
   if (training)
     bn_reduce_kernel<<<dim3(events, cdiv(c, 8)), 256, 0, st>>>(partials, tiles_per_event, (double)count_per_event, c,
                                                                  mean_out, rstd_out);

@@ -193,36 +193,52 @@ __global__ void __launch_bounds__(256) contrastive_fwd_kernel(const float* embed
   if (threadIdx.x == 0) saved[2 * seq * seq + 4 * seq] = t / seq;
 }
 
+// grid (events, column slices of SLICE features): the 40 x dim gradient of an event is independent per
+// feature column, so the columns are spread over the chip instead of one CTA per event
+constexpr int CBWD_SLICE = 64;
 __global__ void __launch_bounds__(256) contrastive_bwd_kernel(const float* embed, const float* proxy,
                                                               const float* saved_all, const float* dloss, int events,
                                                               int seq, int dim, float temp, float* dembed,
                                                               float* dproxy) {
   extern __shared__ float sm[];
-  const int e = blockIdx.x;
+  const int e = blockIdx.x, k0 = blockIdx.y * CBWD_SLICE;
   const float* saved = saved_all + (int64_t)e * (2 * seq * seq + 4 * seq + 1);
-  float* A = sm;                 // [seq][seq] coefficient on cos(e_i, e_j), symmetrised
-  float* B = A + seq * seq;      // [seq] coefficient on cos(e_i, p_i)
+  float* A = sm;                 // [seq][seq] coefficient on cos(e_i, e_j), symmetrised, times 1/(|e_i||e_j|)
+  float* A2 = A + seq * seq;     // [seq] sum_j A_ij * cos_ij / |e_i|^2   (coefficient of e_i itself)
+  float* B = A2 + seq;           // [seq] coefficient on cos(e_i, p_i)
+  float* ine = B + seq;          // [seq] 1 / max(|e_i|, eps)
+  float* inp = ine + seq;        // [seq] 1 / max(|p_i|, eps)
   const float* P = saved; const float* Cs = saved + seq * seq;
   const float* q = saved + 2 * seq * seq; const float* cp = q + seq; const float* ne = cp + seq; const float* np_ = ne + seq;
   const float k = dloss[0] / (events * (float)seq * temp);
-  for (int p = threadIdx.x; p < seq * seq; p += blockDim.x) {
-    int i = p / seq, j = p - i * seq;
-    A[p] = k * (P[i * seq + j] + P[j * seq + i]);
+  for (int i = threadIdx.x; i < seq; i += blockDim.x) {
+    ine[i] = 1.f / fmaxf(ne[i], 1e-8f);
+    inp[i] = 1.f / fmaxf(np_[i], 1e-8f);
+    B[i] = -k * (1.f - q[i]);
   }
-  for (int i = threadIdx.x; i < seq; i += blockDim.x) B[i] = -k * (1.f - q[i]);
+  __syncthreads();
+  for (int p = threadIdx.x; p < seq * seq; p += blockDim.x) {
+    const int i = p / seq, j = p - i * seq;
+    A[p] = i == j ? 0.f : k * (P[i * seq + j] + P[j * seq + i]) * ine[i] * ine[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < seq; i += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < seq; ++j) a = fmaf(A[i * seq + j] * fmaxf(ne[j], 1e-8f), Cs[i * seq + j], a);  // A_ij cos_ij / |e_i|
+    A2[i] = a * ine[i];
+  }
   __syncthreads();
   const float* E = embed + (int64_t)e * seq * dim;
   const float* Pr = proxy + (int64_t)e * seq * dim;
-  for (int idx = threadIdx.x; idx < seq * dim; idx += blockDim.x) {
-    int i = idx / dim, kk = idx - i * dim;
-    const float ni = fmaxf(ne[i], 1e-8f), npi = fmaxf(np_[i], 1e-8f);
-    const float ei = E[idx], pi = Pr[idx];
-    float g = 0.f;
-    for (int j = 0; j < seq; ++j)
-      if (j != i) g = fmaf(A[i * seq + j], E[(int64_t)j * dim + kk] / (ni * fmaxf(ne[j], 1e-8f)) - Cs[i * seq + j] * ei / (ni * ni), g);
-    g = fmaf(B[i], pi / (ni * npi) - cp[i] * ei / (ni * ni), g);
-    dembed[(int64_t)e * seq * dim + idx] = g;
-    if (dproxy) dproxy[(int64_t)e * seq * dim + idx] = B[i] * (ei / (ni * npi) - cp[i] * pi / (npi * npi));
+  const int ncol = dim - k0 < CBWD_SLICE ? dim - k0 : CBWD_SLICE;
+  for (int idx = threadIdx.x; idx < seq * ncol; idx += blockDim.x) {
+    const int i = idx / ncol, kk = k0 + idx - i * ncol;
+    const float ei = E[(int64_t)i * dim + kk], pi = Pr[(int64_t)i * dim + kk];
+    float g = -A2[i] * ei;
+    for (int j = 0; j < seq; ++j) g = fmaf(A[i * seq + j], E[(int64_t)j * dim + kk], g);
+    g = fmaf(B[i], pi * ine[i] * inp[i] - cp[i] * ei * ine[i] * ine[i], g);
+    dembed[(int64_t)e * seq * dim + (int64_t)i * dim + kk] = g;
+    if (dproxy) dproxy[(int64_t)e * seq * dim + (int64_t)i * dim + kk] = B[i] * (ei * ine[i] * inp[i] - cp[i] * pi * inp[i] * inp[i]);
   }
 }
 
@@ -361,8 +377,8 @@ int iea_loss_contrastive_fwd(const float* embed, const float* proxy, int events,
 int iea_loss_contrastive_bwd(const float* embed, const float* proxy, const float* saved, const float* dloss,
                              int events, int seq, int dim, float temperature, float* dembed, float* dproxy,
                              iea_stream_t st) {
-  size_t smem = (size_t)(seq * seq + seq) * sizeof(float);
-  contrastive_bwd_kernel<<<events, 256, smem, (cudaStream_t)st>>>(embed, proxy, saved, dloss, events, seq, dim,
+  size_t smem = (size_t)(seq * seq + 4 * seq) * sizeof(float);
+  contrastive_bwd_kernel<<<dim3(events, cdiv(dim, CBWD_SLICE)), 256, smem, (cudaStream_t)st>>>(embed, proxy, saved, dloss, events, seq, dim,
                                                                   temperature, dembed, dproxy);
   return check_launch("iea_loss_contrastive_bwd");
 }
