@@ -15,6 +15,7 @@
 // has ~1400 issue slots per tile at the HBM rate, so 64-bit div/mod per chunk would dominate.
 // Layers whose weights do not fit (>= 128-channel 3x3, 512-channel 1x1) use the streaming kernel.
 #include "tc_common.cuh"
+#include <type_traits>
 #include <stdlib.h>
 using namespace iea;
 
@@ -48,6 +49,16 @@ __device__ long long g_trace[8][512];
 #define TRACE(slot, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_trace[slot][idx] = clock64(); } while (0)
 #else
 #define TRACE(slot, idx) do { } while (0)
+#endif
+
+// ablation switches of the profiling builds (-DIEA_THIN_DBG, IEA_TC2_DBG bits as in tools/ablate.py);
+// compiled out of the product kernel
+#ifdef IEA_THIN_DBG
+#define DBG(bit) (p.dbg & (bit))
+#define DBG_ANY (p.dbg != 0)
+#else
+#define DBG(bit) 0
+#define DBG_ANY 0
 #endif
 
 struct Params {
@@ -207,7 +218,7 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
             for (int j = 0; j < CPR / 2; ++j) {
               const uint64_t da = da_base + (a_tap + 2 * j * plane16);
               const uint64_t db = db_base + (b_tap + 2 * j * lbo16);
-              if (!(p.dbg & 2)) tc_mma(tacc, da, db, idesc, (kb > 0 || tap > 0 || j > 0) ? 1u : 0u);
+              if (!DBG(2)) tc_mma(tacc, da, db, idesc, (kb > 0 || tap > 0 || j > 0) ? 1u : 0u);
             }
           }
           tc_commit(empty_bar(s));
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
         if (IS3) base = ((int64_t)(c.t.n * p.hs + ((c.t.th * 16) >> sh_)) * p.ws + ((c.t.tw * 8) >> sh_)) * d.x_ld + ci;
         else base = (int64_t)(tile0 + c.tl) * BM * d.x_ld + ci;
         const bf16* bp = xb + base;
-        if (!(p.dbg & 16)) {
+        if (!DBG(16)) {
 #pragma unroll
           for (int i = 0; i < NL; ++i)
             if (i < NL - 1 || last_ok)
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
           const float v = cc == 0 ? ld_act(d.x, d.x_dtype, pix * d.x_ld) : 0.f;
           const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(a1 + i * GP * 16), "r"(lo), "r"(0) : "memory");
-        } else if (in && !(p.dbg & 16)) {
+        } else if (in && !DBG(16)) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a1 + i * GP * 16), "l"(xb + pix * d.x_ld + ci) : "memory");
         } else {
           asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a1 + i * GP * 16), "r"(0) : "memory");
@@ -355,7 +366,7 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
           const bool in = coords_slow(o, pp, nn, ih, iw);
           *reinterpret_cast<uint4*>(a1 + i * GP * 16) = in ? load_chunk(d, p.hs, p.ws, nn, ih, iw, ci) : make_uint4(0, 0, 0, 0);
         }
-      } else if ((affine || relu) && !(p.dbg & 1)) {  // in-place fused prologue on the chunks this thread copied
+      } else if ((affine || relu) && !DBG(1)) {  // in-place fused prologue on the chunks this thread copied
         const int nn = c.t.n;  // (affine on a 1x1 layer implies uniform_n, so the cursor's image index is exact)
         if (affine && (nn != ss_n || ci != ss_ci)) {
           float sc[8], sh[8];
@@ -547,8 +558,8 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
           uint32_t o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = pack2(v[j].x, v[j].y);
-          if (!(p.dbg & 4)) { yp[0] = make_uint4(o[0], o[1], o[2], o[3]); yp[1] = make_uint4(o[4], o[5], o[6], o[7]); }
-          if (has_stats && !(p.dbg & 8)) {
+          if (!DBG(4)) { yp[0] = make_uint4(o[0], o[1], o[2], o[3]); yp[1] = make_uint4(o[4], o[5], o[6], o[7]); }
+          if (has_stats && !DBG(8)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s1[cb * 8 + j] = fadd2(s1[cb * 8 + j], v[j]); s2[cb * 8 + j] = ffma2(v[j], v[j], s2[cb * 8 + j]); }
           }
@@ -566,6 +577,138 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
     int parts = 1;
     while (parts * 2 * cg <= 128) parts *= 2;
     const int rows_per = BM / parts;
+    // ---- fast staged epilogue: the shapes of the generator / discriminator main path (no accumulate, no
+    // activation, residual absent / same-resolution / nearest-up2).  Straight-line per flavour (compile-time
+    // residual and statistics switches), packed fp32x2 math, copy-out with per-thread constant strides, and
+    // the batch-norm partial sums taken from the 16-byte chunks while they are copied out (no second pass).
+    const bool fast = d.acc_c0 < 0 && d.act == IEA_ACT_NONE && d.cout >= 16 && cg_pow2 && cg <= 32 &&
+                      (!d.res || d.res_mode != IEA_IN_POOL2) && !DBG_ANY;
+    auto fast_loop = [&](auto res_c_, auto stats_c_) {
+      constexpr bool RES = decltype(res_c_)::value, STATS = decltype(stats_c_)::value;
+      const int g8 = et & (cg - 1), r0 = et >> cg_sh, step = 128 >> cg_sh;  // copy-out: rows r0, r0+step, ... of chunk g8
+      const bf16* const rp_ = (const bf16*)d.res;
+      bf16* const yb = (bf16*)d.y;
+      const int ncb = p.BN / 16;
+      for (int tcount = 0; tcount < my_tiles; ++tcount) {
+        const int tile = tile0 + tcount;
+        const Origin o = tile_origin<IS3>(p, tile);
+        const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+        int64_t m; int nn = 0, oh = 0, ow = 0; bool valid = true;
+        if (IS3) {
+          nn = o.n; oh = o.h0 + (et >> 3); ow = o.w0 + (et & 7);
+          m = ((int64_t)nn * d.h + oh) * d.w + ow;
+        } else {
+          m = o.m0 + et;
+          valid = m < p.M;
+          if (RES && valid && need_px) {
+            const unsigned mm = (unsigned)m, t = fdiv(mm, p.fd_w);
+            ow = (int)(mm - t * (unsigned)d.w); nn = (int)fdiv(t, p.fd_h); oh = (int)(t - (unsigned)nn * (unsigned)d.h);
+          }
+        }
+        const bf16* rrow = nullptr;
+        uint4 pr0, pr1;
+        if (RES && valid) {
+          rrow = d.res_mode == IEA_IN_UP2 ? rp_ + (((int64_t)nn * (d.h >> 1) + (oh >> 1)) * (d.w >> 1) + (ow >> 1)) * d.res_ld
+                                          : rp_ + m * d.res_ld;
+          if (0 < d.res_c) { pr0 = __ldg(reinterpret_cast<const uint4*>(rrow)); pr1 = __ldg(reinterpret_cast<const uint4*>(rrow + 8)); }
+        }
+        mbar_wait(tfull_bar(ab), aph);
+        tc_fence_after();
+        uint8_t* const srow = stg + (size_t)et * p.staging_ld;
+        for (int cb = 0; cb < ncb; ++cb) {
+          const int c0 = cb * 16;
+          uint32_t raw[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]), "=r"(raw[6]), "=r"(raw[7]),
+                "=r"(raw[8]), "=r"(raw[9]), "=r"(raw[10]), "=r"(raw[11]), "=r"(raw[12]), "=r"(raw[13]), "=r"(raw[14]), "=r"(raw[15])
+              : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.BN + c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float2 v[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(ep_sc + c0 + 4 * j4);
+            const float4 b4 = *reinterpret_cast<const float4*>(ep_bs + c0 + 4 * j4);
+            v[2 * j4] = ffma2(make_float2(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1])), make_float2(s4.x, s4.y),
+                              make_float2(b4.x, b4.y));
+            v[2 * j4 + 1] = ffma2(make_float2(__uint_as_float(raw[4 * j4 + 2]), __uint_as_float(raw[4 * j4 + 3])),
+                                  make_float2(s4.z, s4.w), make_float2(b4.z, b4.w));
+          }
+          if (RES) {
+            if (valid && c0 < d.res_c) {
+              const uint32_t w[8] = {pr0.x, pr0.y, pr0.z, pr0.w, pr1.x, pr1.y, pr1.z, pr1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
+            }
+            if (valid && cb + 1 < ncb && c0 + 16 < d.res_c) {  // next block's residual: in flight during pack + staging store
+              pr0 = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 16));
+              pr1 = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 24));
+            }
+          }
+          uint4 o0, o1;
+          if (valid) {
+            o0 = make_uint4(pack2(v[0].x, v[0].y), pack2(v[1].x, v[1].y), pack2(v[2].x, v[2].y), pack2(v[3].x, v[3].y));
+            o1 = make_uint4(pack2(v[4].x, v[4].y), pack2(v[5].x, v[5].y), pack2(v[6].x, v[6].y), pack2(v[7].x, v[7].y));
+          } else {
+            o0 = make_uint4(0, 0, 0, 0); o1 = o0;  // rows beyond the last pixel: zeros (they enter the statistics)
+          }
+          *reinterpret_cast<uint4*>(srow + cb * 32) = o0;
+          *reinterpret_cast<uint4*>(srow + cb * 32 + 16) = o1;
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(ab));  // accumulator drained: the MMA warp may start the next tile
+        bar_sync_epi();
+        // coalesced copy-out: this thread moves chunk g8 of rows r0, r0 + step, ... (cg rows) -- rows of the tile
+        // are contiguous pixel runs in NHWC -- and sums its chunks for the batch-norm statistics on the way
+        float2 s1[4], s2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = s1[j]; }
+        {
+          const uint8_t* sp = stg + (size_t)r0 * p.staging_ld + g8 * 16;
+          const size_t sstep = (size_t)step * p.staging_ld;
+          bf16* yp; int64_t ystep; int rows_left = cg;
+          if (IS3) {  // row r -> pixel (r >> 3, r & 7) of the 16x8 tile; step is 4, 8 or 16 rows
+            yp = yb + (((int64_t)o.n * d.h + o.h0 + (r0 >> 3)) * d.w + o.w0 + (r0 & 7)) * d.y_ld + g8 * 8;
+            ystep = (int64_t)(step >> 3) * d.w * d.y_ld;  // (step >= 8 on this path: Cout <= 128 for 3x3)
+          } else {
+            yp = yb + (o.m0 + r0) * d.y_ld + g8 * 8;
+            ystep = (int64_t)step * d.y_ld;
+            const int64_t left = p.M - o.m0 - r0;  // rows of this tile that exist, from r0 on
+            if (left < (int64_t)(cg - 1) * step + 1) rows_left = left <= 0 ? 0 : (int)((left - 1) / step) + 1;
+          }
+          for (int it = 0; it < rows_left; ++it) {
+            const uint4 v4 = *reinterpret_cast<const uint4*>(sp);
+            *reinterpret_cast<uint4*>(yp) = v4;
+            if (STATS) {
+              const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = bf2_to_f2(w[j]); s1[j] = fadd2(s1[j], f); s2[j] = ffma2(f, f, s2[j]); }
+            }
+            sp += sstep; yp += ystep;
+          }
+        }
+        if (STATS) {  // [part = r0][BN][2] partials, then a fixed-order fold over the parts
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            stat[(r0 * p.BN + g8 * 8 + 2 * j) * 2] = s1[j].x; stat[(r0 * p.BN + g8 * 8 + 2 * j) * 2 + 1] = s2[j].x;
+            stat[(r0 * p.BN + g8 * 8 + 2 * j + 1) * 2] = s1[j].y; stat[(r0 * p.BN + g8 * 8 + 2 * j + 1) * 2 + 1] = s2[j].y;
+          }
+          bar_sync_epi();
+          for (int c = et; c < p.BN * 2; c += 128) {
+            float a = 0.f;
+            for (int part = 0; part < step; ++part) a += stat[part * p.BN * 2 + c];
+            d.stats[(int64_t)tile * d.cout * 2 + c] = a;
+          }
+        }
+        bar_sync_epi();  // staging / stat scratch are reused by the next tile
+      }
+    };
+    if (fast) {
+      if (d.res && d.stats) fast_loop(std::true_type{}, std::true_type{});
+      else if (d.res) fast_loop(std::true_type{}, std::false_type{});
+      else if (d.stats) fast_loop(std::false_type{}, std::true_type{});
+      else fast_loop(std::false_type{}, std::false_type{});
+    } else
     for (int tcount = 0; tcount < my_tiles; ++tcount) {
       const int tile = tile0 + tcount;
       const Origin o = tile_origin<IS3>(p, tile);
