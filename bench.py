@@ -335,7 +335,9 @@ def main():
         y = torch.arange(40, device=dev).repeat(ev)
         xh = (torch.rand(n, 1, 256, res_w) * 2 - 1).pin_memory()
         yh = torch.arange(40).repeat(ev).pin_memory()
-        kt, wt = (K_, W) if args.workload == "train" else (max(2, min(K_, 3)), 3)
+        # (the extra uses 6 warm-up steps: the caching allocator and first-call kernel set-up need more than 3
+        #  full G+D steps to settle -- 3 warm-ups measured 246 ms where the settled step is 202 ms)
+        kt, wt = (K_, W) if args.workload == "train" else (max(2, min(K_, 4)), max(W, 6))
         l0 = E_.LAUNCHES[0]
         if args.workload == "train":
             sampler.start()

@@ -30,6 +30,12 @@ class SnLayer(C.Structure):
                 ("scratch_off", i64)]
 
 
+class SnBwdItem(C.Structure):
+    _fields_ = [("gpart", vp), ("w", vp), ("u", vp), ("v", vp), ("inv_sigma", vp), ("dw", vp),
+                ("nsplit", i32), ("spectral", i32), ("rows", i32), ("cin", i32), ("taps", i32), ("beta", f32),
+                ("block0", i32), ("nblocks", i32)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("n", i64), ("h", i32), ("w", i32), ("cin", i32), ("cout", i32), ("ksize", i32),
                 ("x", vp), ("x_dtype", i32), ("x_ld", i32), ("in_mode", i32), ("in_relu", i32),
@@ -52,6 +58,7 @@ _SIG = {
     "iea_sm_count": [i32],
     "iea_sn_power_iter": [vp, i32, vp, i32, vp, i32, vp],
     "iea_sn_weight_bwd": [vp, i32, vp, vp, vp, vp, i32, vp, f32, i32, i32, i32, vp, vp],
+    "iea_sn_weight_bwd_grouped": [vp, i32, i32, vp, vp],
     "iea_conv_fprop": [vp, vp],
     "iea_conv_tc_supported": [vp],
     "iea_conv_stats_slots": [vp],

@@ -217,36 +217,42 @@ __global__ void __launch_bounds__(256) bn_finalize_fused_kernel(const float* par
   __syncthreads();
   if (!last) return;
   __threadfence();
-  float* rs_s = reinterpret_cast<float*>(r1);  // [events][8] rstd of this channel group (events <= 64)
+  // (everything below runs in ONE block per channel group: keep it off the memory-latency chain -- the
+  //  per-event statistics are staged in shared memory by all threads first, the sequential running-statistics
+  //  recursion then reads shared memory only)
+  __shared__ float rs_s[512];                   // [events][8] rstd
+  float* m_s = reinterpret_cast<float*>(r1);    // [events][8] mean      (events <= 64)
+  float* v_s = reinterpret_cast<float*>(r2);    // [events][8] biased variance
+  for (int i = threadIdx.x; i < events * 8; i += 256) {
+    const int ev = i >> 3, ch = blockIdx.y * 8 + (i & 7);
+    float mu = 0.f, var = 0.f;
+    if (ch < c) { mu = __ldcg(mean_io + ev * c + ch); var = __ldcg(rstd_io + ev * c + ch); }
+    m_s[i] = mu; v_s[i] = var;
+    rs_s[i] = (float)(1.0 / sqrt((double)var + (double)eps));
+  }
+  __syncthreads();
   if (tl == 0 && cc < c) {
     float rm = stored_mean ? stored_mean[cc] : 0.f, rv = stored_var ? stored_var[cc] : 1.f;
     for (int ev = 0; ev < events; ++ev) {
-      const double var = (double)__ldcg(rstd_io + ev * c + cc);
+      const double var = (double)v_s[ev * 8 + cl];
       const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-      rm = (1.f - momentum) * rm + momentum * __ldcg(mean_io + ev * c + cc);
+      rm = (1.f - momentum) * rm + momentum * m_s[ev * 8 + cl];
       rv = (1.f - momentum) * rv + momentum * (float)unb;
     }
     if (stored_mean) { stored_mean[cc] = rm; stored_var[cc] = rv; }
   }
   for (int i = threadIdx.x; i < events * 8; i += 256) {
     const int ev = i >> 3, ch = blockIdx.y * 8 + (i & 7);
-    if (ch < c) {
-      const float rstd = (float)(1.0 / sqrt((double)__ldcg(rstd_io + ev * c + ch) + (double)eps));
-      if (ev < 64) rs_s[ev * 8 + (i & 7)] = rstd;
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < events * 8; i += 256) {
-    const int ev = i >> 3, ch = blockIdx.y * 8 + (i & 7);
-    if (ch < c) rstd_io[ev * c + ch] = rs_s[ev * 8 + (i & 7)];
+    if (ch < c) rstd_io[ev * c + ch] = rs_s[i];
   }
   const int64_t nimg = (int64_t)events * imgs;
+#pragma unroll 4
   for (int64_t i = threadIdx.x; i < nimg * 8; i += 256) {
     const int64_t n = i >> 3;
     const int ch = blockIdx.y * 8 + (int)(i & 7);
     if (ch >= c) continue;
     const int ev = (int)(n / imgs);
-    const float rstd = rs_s[ev * 8 + (i & 7)], mean = __ldcg(mean_io + ev * c + ch);
+    const float rstd = rs_s[ev * 8 + (i & 7)], mean = m_s[ev * 8 + (i & 7)];
     const float gn = gain_add + (gain ? gain[n * gain_ld + ch] : 0.f);
     const float bs = bias ? bias[n * bias_ld + ch] : 0.f;
     const float sc = rstd * gn;

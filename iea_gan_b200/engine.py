@@ -96,6 +96,7 @@ class Tape:
         self.record = record
         self.nodes = []
         self.pgrads = {}
+        self.sn_jobs = []  # deferred W/sigma backward of the layers of this pass: one grouped launch
 
     def add(self, fn):
         if self.record:
@@ -105,10 +106,35 @@ class Tape:
         for fn in reversed(self.nodes):
             fn()
         self.nodes = []
+        self.flush_sn()
+
+    def sn_weight_bwd(self, gp, nsplit, layer, saved, dw):
+        """Queue dW = G/sigma - (<G,W>/sigma^2) u v^T for one layer (iea_sn_weight_bwd_grouped)."""
+        isg, u_, v_ = saved
+        self.sn_jobs.append((gp, nsplit, layer.weight, u_, v_, isg, layer.spectral, dw, layer.rows, layer.cin, layer.taps))
+
+    def flush_sn(self):
+        jobs, self.sn_jobs = self.sn_jobs, []
+        if not jobs:
+            return
+        items = (L.SnBwdItem * len(jobs))()
+        b0 = 0
+        for it, (gp, nsplit, w, u_, v_, isg, spectral, dw, rows, cin, taps) in zip(items, jobs):
+            nb = max(1, min(256, (rows * cin * taps + 1023) // 1024))
+            it.gpart, it.w, it.u, it.v, it.inv_sigma, it.dw = ptr(gp), ptr(w), ptr(u_), ptr(v_), ptr(isg), ptr(dw)
+            it.nsplit, it.spectral, it.rows, it.cin, it.taps, it.beta = nsplit, spectral, rows, cin, taps, 0.0
+            it.block0, it.nblocks = b0, nb
+            b0 += nb
+        dev = jobs[0][7].device
+        host = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).pin_memory()
+        table = host.to(dev, non_blocking=True)
+        K("iea_sn_weight_bwd_grouped", ptr(table), len(jobs), b0, ptr(_f32(b0, dev)), L.stream(), launches=2)
+        self._sn_keep = (host, table)  # (stream-ordered allocators make dropping the job tensors safe once enqueued)
 
     def pgrad(self, param, g):
         k = id(param)
         if k in self.pgrads:
+            self.flush_sn()  # (an accumulation reads the gradient a queued job has not written yet)
             acc = self.pgrads[k]
             K("iea_axpby", ptr(g), L.F32, 1.0, ptr(acc), L.F32, 1.0, ptr(acc), L.F32, g.numel(), L.stream())
         else:
@@ -448,8 +474,7 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
                 if l.weight.requires_grad:
                     dw = torch.empty_like(l.weight)
                     gp = gpart if len(wls) == 1 else gpart[:, r0:r0 + l.rows].contiguous()
-                    K("iea_sn_weight_bwd", ptr(gp), nsplit, ptr(l.weight), ptr(u_), ptr(v_), ptr(isg), l.spectral,
-                      ptr(dw), 0.0, l.rows, l.cin, l.taps, ptr(_f32(520, dev)), L.stream(), launches=2)
+                    tape.sn_weight_bwd(gp, nsplit, l, (isg, u_, v_), dw)
                     tape.pgrad(l.weight, dw)
                 r0 += l.rows
         if need_db:

@@ -78,6 +78,17 @@ int iea_sn_weight_bwd(const float* gpart, int nsplit, const float* w, const floa
                       const float* inv_sigma, int spectral, float* dw, float beta, int rows, int cin,
                       int taps, float* scratch /* >= 2 + 2*gridcap floats */, iea_stream_t stream);
 
+/* the same for many layers in two launches: items live in device memory, sorted by block0; item i owns the
+ * blocks [block0, block0 + nblocks) of the grid of total_blocks (nblocks = ceil(rows*cin*taps / 1024), <= 256);
+ * scratch >= total_blocks floats. */
+typedef struct {
+  const float* gpart; const float* w; const float* u; const float* v; const float* inv_sigma; float* dw;
+  int32_t nsplit, spectral, rows, cin, taps; float beta;
+  int32_t block0, nblocks;
+} iea_sn_bwd_item;
+int iea_sn_weight_bwd_grouped(const iea_sn_bwd_item* items_dev, int n_items, int total_blocks, float* scratch,
+                              iea_stream_t stream);
+
 /* ---- fused convolution / linear: layers.py:197-206 SNConv2d.forward, :223-224 SNLinear ----
  * y = act( conv_k(T(x), Wpack) * out_scale + bias + residual ), with
  *   T(x) = [avgpool2 | nearest-up2]( relu?( x * in_scale[n][c] + in_shift[n][c] ) )
