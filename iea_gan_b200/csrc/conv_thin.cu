@@ -17,7 +17,9 @@
 // Shapes outside this envelope (pooled inputs, Cout > 32, Cin > 64, the 1-channel stem) stay on
 // conv_tc2.cu / conv_tc.cu.
 #include "tc_common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 using namespace iea;
 
 namespace thin {
@@ -45,7 +47,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
 }
 
 // compile-time geometry shared by the kernel and the launcher
-template <int CPR, bool IS3, int MT>
+template <int CPR, bool IS3, int MT, bool TMA = false>
 struct Geo {
   static constexpr int PW = 8 * MT + 2;                       // patch pitch in pixels (3x3)
   static constexpr int NPIX = IS3 ? 18 * PW : BM * MT;        // staged pixels per macro tile
@@ -53,7 +55,9 @@ struct Geo {
   static constexpr int NS = (NCH + 127) / 128;                // chunk slots per producer thread
   // planes (8 channels each) are skewed by 128/CPR bytes so that the CPR chunks of a pixel, written by
   // consecutive threads, fall into different shared-memory banks
-  static constexpr uint32_t PLANE = (NPIX * 16 + 127) / 128 * 128 + 128 / CPR;
+  // (TMA box loads write whole planes: no skew there, the transform threads walk a plane pixel by pixel instead)
+  static constexpr uint32_t PLANE = (NPIX * 16 + 127) / 128 * 128 + (TMA ? 0 : 128 / CPR);
+  static constexpr uint32_t BOX_BYTES = NPIX * 16;            // bytes one plane receives per macro tile
   static constexpr uint32_t STAGE = (CPR * PLANE + 127) / 128 * 128;
 };
 
@@ -132,9 +136,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // compiler shuffle the 16 accumulator registers at every merge point: ~200 instructions per 128x16 block
 // where ~70 do the work).  1: scale/bias + residual read, same-resolution or nearest-up2 [+ statistics]
 // (the GBlock conv4 layers);  2: everything (pooled residual, accumulate, activation, padded 1-channel store)
-template <int CPR, bool IS3, int NB, int MT, int EPI>
-__global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_constant__ Params p) {
-  using G = Geo<CPR, IS3, MT>;
+// TMA: same-resolution inputs are fetched by TMA box loads, one per 8-channel plane ({8 ch, patch width, 18 rows}
+// for 3x3 with out-of-image pixels zero-filled by the unit; {8 ch, 128 pixels} for 1x1): one elected thread per
+// producer group issues them, the other producer threads only run the fused prologue (nothing at all for the
+// prologue-free data-gradient convolutions).  Nearest-up2 inputs keep the cp.async slot tables.
+template <int CPR, bool IS3, int NB, int MT, int EPI, bool TMA>
+__global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_constant__ Params p,
+                                                               const __grid_constant__ CUtensorMap tmap) {
+  using G = Geo<CPR, IS3, MT, TMA>;
   constexpr int PW = G::PW, NCH = G::NCH, NS = G::NS;
   constexpr uint32_t PLANE = G::PLANE, STAGE = G::STAGE;
   constexpr int TAPS = IS3 ? 9 : 1;
@@ -149,12 +158,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
   // barriers: full[S] | empty[S] | tfull[4] | tempty[4] | w
   const uint32_t full0 = bar0, empty0 = bar0 + 8u * S, tfull0 = bar0 + 16u * S, tempty0 = tfull0 + 32, w_bar = tfull0 + 64;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.bar_off + 16 * S + 72);
+  const uint32_t land0 = bar0 + 16u * S + 80;  // land[S]: TMA completion (transaction bytes) per ring slot
 
   if (tid == 0) {
     // one arrival per WARP on full / tempty (per-thread arrivals would wake every parked waiter 128 times)
     for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 4); mbar_init(empty0 + 8 * s, NI); }
     for (int b = 0; b < 4; ++b) { mbar_init(tfull0 + 8 * b, NI); mbar_init(tempty0 + 8 * b, 4); }
     mbar_init(w_bar, 1);
+    if (TMA) for (int s = 0; s < S; ++s) mbar_init(land0 + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -176,7 +187,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
     // ===================== patch producers: two groups of 4 warps, alternate macro tiles =====================
     const int grp = warp >> 2, pw = warp & 3;
     const int pt = tid & 127;
-    const int cc = pt % CPR;                                   // this thread's 8-channel plane (fixed: 128 % CPR == 0)
+    // this thread's 8-channel plane (fixed: 128 % CPR == 0).  cp.async: the CPR chunks of a pixel go to consecutive
+    // threads (coalesced global reads); TMA: a thread walks one plane, consecutive threads = consecutive pixels
+    constexpr int TPP = 128 / CPR;                             // threads per plane (TMA mapping)
+    const int cc = TMA ? pt / TPP : pt % CPR;
     const bool affine = d.in_scale != nullptr;
     const bool relu = d.in_relu != 0;
     const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
@@ -189,8 +203,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       const int q = pt + 128 * i;
-      const int pp = q / CPR;  // patch pixel
-      if (q < NCH) m_valid |= 1u << i;
+      const int pp = TMA ? (pt % TPP) + TPP * i : q / CPR;  // patch pixel
+      if (TMA ? pp < G::NPIX : q < NCH) m_valid |= 1u << i;
       if (IS3) {
         const int pi = pp / PW, pj = pp - pi * PW;
         goff[i] = (((pi - 1) >> sh_) * p.ws + ((pj - 1) >> sh_)) * d.x_ld + cc * 8;
@@ -225,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       uint32_t m = 0;
 #pragma unroll
       for (int i = 0; i < NS; ++i)
-        if ((pt + 128 * i) / CPR >= left) m |= 1u << i;
+        if ((TMA ? (pt % TPP) + TPP * i : (pt + 128 * i) / CPR) >= left) m |= 1u << i;
       return m;
     };
     auto issue = [&](const Cur& c) {
@@ -249,6 +263,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
           if (pad >> i & 1) asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a + soff[i]), "r"(0) : "memory");
           else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a + soff[i]), "l"(bp + goff[i]) : "memory");
         }
+      }
+    };
+
+    auto issue_tma = [&](const Cur& c) {  // one thread per group
+      mbar_wait(empty0 + 8 * c.s, c.ph ^ 1);
+      const uint32_t a = st0 + c.s * STAGE, bar = land0 + 8 * c.s;
+      mbar_expect_tx(bar, CPR * G::BOX_BYTES);
+      const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);
+      if (IS3) {
+        const int w0 = c.c.tw * (8 * MT) - 1, h0 = c.c.th * 16 - 1;
+#pragma unroll
+        for (int k = 0; k < CPR; ++k)
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                       ::"r"(a + k * PLANE), "l"(tm), "r"(k * 8), "r"(w0), "r"(h0), "r"(c.c.n), "r"(bar) : "memory");
+      } else {
+        const int m0 = (g0 + c.t) * (BM * MT);
+#pragma unroll
+        for (int k = 0; k < CPR; ++k)
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(a + k * PLANE + j * (BM * 16)), "l"(tm), "r"(k * 8), "r"(m0 + j * BM), "r"(bar) : "memory");
       }
     };
 
@@ -297,18 +333,30 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
     ci.s = grp; ci.ph = 0; ci.t = grp; ci.c = pos_of(p, g0 + grp);
     ct = ci;
     for (int k = 0; k < D - 1; ++k) {
-      if (ci.t < my_n) { issue(ci); cur_next(ci); }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (ci.t < my_n) {
+        if (!TMA) issue(ci);
+        else if (pt == 0) issue_tma(ci);
+        cur_next(ci);
+      }
+      if (!TMA) asm volatile("cp.async.commit_group;" ::: "memory");
     }
     __nv_bfloat162 sc2[4], sh2[4];
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     int ss_n = -1;
     for (; ct.t < my_n;) {
-      if (ci.t < my_n) { issue(ci); cur_next(ci); }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
-      else asm volatile("cp.async.wait_group 3;" ::: "memory");
+      if (ci.t < my_n) {
+        if (!TMA) issue(ci);
+        else if (pt == 0) issue_tma(ci);
+        cur_next(ci);
+      }
+      if (!TMA) {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else asm volatile("cp.async.wait_group 3;" ::: "memory");
+      } else {
+        mbar_wait(land0 + 8 * ct.s, ct.ph);  // the boxes of this macro tile have landed
+      }
       if (pt == 0) TRACE(0, ct.t);
       if ((affine || relu) && !DBG(1)) {  // fused prologue, in place on the chunks this thread copied
         if (affine && ct.c.n != ss_n) {
@@ -359,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       if (pw < NI) mma_item(ct.t, ct.s, ct.ph);
       cur_next(ct);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!TMA) asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
     // ===================== epilogue: two groups of 4 warps, alternate macro tiles; one pixel per thread =====================
     const int grp = (warp - 8) >> 2;
@@ -626,9 +674,42 @@ int iea_conv_thin_ok(const iea_conv_desc* d) {
   return 1;
 }
 
-template <int CPR, bool IS3, int MT>
+// ---- TMA tensor map of the input (driver entry point: the library does not link libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn tma_encoder() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+// {8 channels, patch width, 18 rows, 1 image} boxes of the NHWC input for 3x3; {8 channels, 128 pixels} for 1x1
+static bool thin_tensor_map(const iea_conv_desc* d, bool is3, int mt, CUtensorMap* tm) {
+  encode_tiled_fn enc = tma_encoder();
+  if (!enc) return false;
+  const cuuint64_t ld = (cuuint64_t)d->x_ld * 2;
+  if (is3) {
+    const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    const cuuint64_t strides[3] = {ld, ld * d->w, ld * d->w * d->h};
+    const cuuint32_t box[4] = {8, (cuuint32_t)(8 * mt + 2), 18, 1}, es[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)d->cin, (cuuint64_t)(d->n * (int64_t)d->h * d->w)};
+  const cuuint64_t strides[1] = {ld};
+  const cuuint32_t box[2] = {8, 128}, es[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CPR, bool IS3, int MT, bool TMA>
 static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint32_t& smem) {
-  using G = thin::Geo<CPR, IS3, MT>;
+  using G = thin::Geo<CPR, IS3, MT, TMA>;
   p.d = *d;
   p.wtc = (const bf16*)d->wpack_tc;
   { const char* e_ = getenv("IEA_TC2_DBG"); p.dbg = e_ ? atoi(e_) : 0; }  // profiling ablations only
@@ -653,14 +734,14 @@ static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint
   p.w_bytes = (uint32_t)(cout_e * d->cin * taps * 2);
   p.stage_off = (p.w_bytes + 127) / 128 * 128;
   const uint32_t misc = (2 * cout_e + 2 * 4 * 2 * cout_e) * 4;  // scale, bias, statistics fold of both groups
-  const uint32_t tail = misc + 256;
+  const uint32_t tail = misc + 512;
   int stages = 8;  // even: the two producer groups own alternate ring slots
   while (stages > 4 && p.stage_off + stages * G::STAGE + tail > 200 * 1024) stages -= 2;
   p.stages = stages;
   p.depth = stages >= 8 ? 3 : 2;  // items each group keeps in flight (it owns stages/2 slots)
   p.misc_off = p.stage_off + stages * G::STAGE;
   p.bar_off = (p.misc_off + misc + 15) / 16 * 16;
-  smem = p.bar_off + 256;
+  smem = p.bar_off + 512;  // barriers: full, empty, landing (8 B x stages each), 2 x 4 accumulator, weights; TMEM slot
   uint32_t cols = 32;
   while (cols < (uint32_t)(4 * MT * cout_e)) cols <<= 1;
   p.tmem_cols = cols;
@@ -676,21 +757,36 @@ static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint
 template <int CPR, bool IS3, int NB, int MT>
 static int thin_launch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
   thin::Params p; int grid = 0; uint32_t smem = 0;
-  int rc = thin_prepare<CPR, IS3, MT>(d, p, grid, smem);
+  alignas(64) CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  // TMA producer: same-resolution bf16 input and a producer-paced shape (16 output channels: with 32 the epilogue
+  // paces the kernel); IEA_THIN_TMA=0 keeps the cp.async producer (tests cover both)
+  bool tma = NB == 1 && !grid_only && d->in_mode == IEA_IN_DIRECT && d->x_ld % 8 == 0;
+  if (tma) { const char* e_ = getenv("IEA_THIN_TMA"); if (e_ && e_[0] == '0') tma = false; }
+  if (tma) tma = thin_tensor_map(d, IS3, MT, &tm);
+  int rc = tma ? thin_prepare<CPR, IS3, MT, NB == 1>(d, p, grid, smem) : thin_prepare<CPR, IS3, MT, false>(d, p, grid, smem);
   if (rc) return rc;
   if (grid_only) { *grid_only = grid; return 0; }
   auto run = [&](auto kern) -> int {
     IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, thin::THREADS, smem, s>>>(p);
+    kern<<<grid, thin::THREADS, smem, s>>>(p, tm);
     return check_launch("iea_conv_fprop(tcgen05 thin)");
   };
   // (a compile-time "plain" flavour measured no faster than the generic one -- without a residual the
   //  producers, not the epilogue, pace these kernels -- so only the residual flavour is specialised)
   const bool simple = d->acc_c0 < 0 && d->act == IEA_ACT_NONE && d->cout != 1;
-  if constexpr (!IS3) {
-    if (simple && d->res && d->res_mode != IEA_IN_POOL2) return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 1>);
+  if constexpr (NB == 1) {
+    if (tma) {
+      if constexpr (!IS3) {
+        if (simple && d->res && d->res_mode != IEA_IN_POOL2) return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 1, true>);
+      }
+      return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 2, true>);
+    }
   }
-  return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 2>);
+  if constexpr (!IS3) {
+    if (simple && d->res && d->res_mode != IEA_IN_POOL2) return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 1, false>);
+  }
+  return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 2, false>);
 }
 
 static int thin_dispatch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {

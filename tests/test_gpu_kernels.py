@@ -251,9 +251,15 @@ def test_conv_tcgen05_matches_generic(eng, variant, cin, cout, k, mode, relu, af
     (64, 32, 3, 0, True, True, None, (16, 16), 40),   # single-tile patches, 8 planes
     (64, 16, 1, 0, True, True, None, (16, 24), 40),   # 1x1 whose images are 3 tiles (macro width falls to 1)
     (32, 32, 1, 0, False, False, None, (12, 20), 40)])  # ragged tail: 9600 pixels = 37.5 macro tiles
-def test_conv_thin_macro_tiles(eng, cin, cout, k, mode, relu, aff, resm, hw, n):
-    """conv_thin.cu (macro-tile tcgen05 kernel for Cin <= 64, Cout 16/32) against the CUDA-core kernel."""
-    _tc_vs_generic(eng, "resident", cin, cout, k, mode, relu, aff, resm, hw, n)
+@pytest.mark.parametrize("producer", ["tma", "cp.async"])
+def test_conv_thin_macro_tiles(eng, producer, cin, cout, k, mode, relu, aff, resm, hw, n):
+    """conv_thin.cu (macro-tile tcgen05 kernel for Cin <= 64, Cout 16/32) against the CUDA-core kernel, with
+    the TMA box-load producer (same-resolution inputs, Cout 16) and with the cp.async slot-table producer."""
+    os.environ["IEA_THIN_TMA"] = "1" if producer == "tma" else "0"
+    try:
+        _tc_vs_generic(eng, "resident", cin, cout, k, mode, relu, aff, resm, hw, n)
+    finally:
+        os.environ.pop("IEA_THIN_TMA", None)
 
 
 def _tc_vs_generic(eng, variant, cin, cout, k, mode, relu, aff, resm, hw, n):
