@@ -761,10 +761,11 @@ static int thin_launch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
   memset(&tm, 0, sizeof(tm));
   // TMA producer: same-resolution bf16 input and a producer-paced shape (16 output channels: with 32 the epilogue
   // paces the kernel); IEA_THIN_TMA=0 keeps the cp.async producer (tests cover both)
-  bool tma = NB == 1 && !grid_only && d->in_mode == IEA_IN_DIRECT && d->x_ld % 8 == 0;
+  constexpr bool TMA_OK = NB == 1 || IS3;  // (Cout 32 1x1: the epilogue paces the kernel, nothing to gain)
+  bool tma = TMA_OK && !grid_only && d->in_mode == IEA_IN_DIRECT && d->x_ld % 8 == 0;
   if (tma) { const char* e_ = getenv("IEA_THIN_TMA"); if (e_ && e_[0] == '0') tma = false; }
   if (tma) tma = thin_tensor_map(d, IS3, MT, &tm);
-  int rc = tma ? thin_prepare<CPR, IS3, MT, NB == 1>(d, p, grid, smem) : thin_prepare<CPR, IS3, MT, false>(d, p, grid, smem);
+  int rc = tma ? thin_prepare<CPR, IS3, MT, TMA_OK>(d, p, grid, smem) : thin_prepare<CPR, IS3, MT, false>(d, p, grid, smem);
   if (rc) return rc;
   if (grid_only) { *grid_only = grid; return 0; }
   auto run = [&](auto kern) -> int {
@@ -775,7 +776,7 @@ static int thin_launch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
   // (a compile-time "plain" flavour measured no faster than the generic one -- without a residual the
   //  producers, not the epilogue, pace these kernels -- so only the residual flavour is specialised)
   const bool simple = d->acc_c0 < 0 && d->act == IEA_ACT_NONE && d->cout != 1;
-  if constexpr (NB == 1) {
+  if constexpr (TMA_OK) {
     if (tma) {
       if constexpr (!IS3) {
         if (simple && d->res && d->res_mode != IEA_IN_POOL2) return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 1, true>);
