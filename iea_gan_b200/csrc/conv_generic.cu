@@ -387,8 +387,9 @@ __device__ __forceinline__ uint4 pack8v(const float* f) {
   for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]); o[i] = *reinterpret_cast<uint32_t*>(&t); }
   return r;
 }
-__global__ void __launch_bounds__(256) conv_input_bwd_vec(const iea_conv_desc d, const Geo g, const bf16* da, bf16* dx,
-                                                          int dx_ld, float beta, float* part, int chunks, int px_per_chunk) {
+__global__ void __launch_bounds__(256) conv_input_bwd_vec(const iea_conv_desc d, const Geo g, const bf16* __restrict__ da,
+                                                          bf16* __restrict__ dx, int dx_ld, float beta, float* part,
+                                                          int chunks, int px_per_chunk) {
   extern __shared__ float red[];  // [lanes][cin][2]
   const int64_t n = blockIdx.y;
   const int cgs = d.cin >> 3, lanes = 256 / cgs;
@@ -404,12 +405,15 @@ __global__ void __launch_bounds__(256) conv_input_bwd_vec(const iea_conv_desc d,
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = d.in_scale[si + j]; sh[j] = d.in_shift[si + j]; }
   }
-  const bf16* xb = (const bf16*)d.x;
+  const bf16* __restrict__ xb = (const bf16*)d.x;
+  // (read-only operands through the non-coherent path + restrict: the unrolled iterations issue their loads
+  //  back to back, four pixels in flight per thread, instead of one load-use round trip per pixel)
   if (pl < lanes)
+#pragma unroll 4
     for (int p = p0 + pl; p < p1; p += lanes) {
       const int xh = p / g.ws, xw = p - xh * g.ws;
       float xv[8], gs[8];
-      unpack8v(*reinterpret_cast<const uint4*>(xb + (n * npx + p) * d.x_ld + c0), xv);
+      unpack8v(__ldg(reinterpret_cast<const uint4*>(xb + (n * npx + p) * d.x_ld + c0)), xv);
       if (d.in_mode == IEA_IN_UP2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) gs[j] = 0.f;
@@ -418,16 +422,16 @@ __global__ void __launch_bounds__(256) conv_input_bwd_vec(const iea_conv_desc d,
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             float t[8];
-            unpack8v(*reinterpret_cast<const uint4*>(da + ((n * d.h + 2 * xh + a) * (int64_t)d.w + 2 * xw + b) * d.cin + c0), t);
+            unpack8v(__ldg(reinterpret_cast<const uint4*>(da + ((n * d.h + 2 * xh + a) * (int64_t)d.w + 2 * xw + b) * d.cin + c0)), t);
 #pragma unroll
             for (int j = 0; j < 8; ++j) gs[j] += t[j];
           }
       } else if (d.in_mode == IEA_IN_POOL2) {
-        unpack8v(*reinterpret_cast<const uint4*>(da + ((n * d.h + (xh >> 1)) * (int64_t)d.w + (xw >> 1)) * d.cin + c0), gs);
+        unpack8v(__ldg(reinterpret_cast<const uint4*>(da + ((n * d.h + (xh >> 1)) * (int64_t)d.w + (xw >> 1)) * d.cin + c0)), gs);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gs[j] *= 0.25f;
       } else {
-        unpack8v(*reinterpret_cast<const uint4*>(da + (n * npx + p) * d.cin + c0), gs);
+        unpack8v(__ldg(reinterpret_cast<const uint4*>(da + (n * npx + p) * d.cin + c0)), gs);
       }
       float o[8];
 #pragma unroll
