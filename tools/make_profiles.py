@@ -61,27 +61,27 @@ if os.path.exists(rep):
     with open(os.path.join(P, "ncu_top_kernel_%s.txt" % R), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on -k regex:conv_thin_kernel -s 12 -c 12 : python tools/prof_sample.py 4 2\n"
                 "# the macro-tile tcgen05 conv launches of the second Generator forward (n = 160 images); the 16->16 3x3 @256x256\n"
-                "# layer of bench.py's `roofline` is conv_thin_kernel<2, 1, 1, 4> with ~336 MB read (same-resolution input)\n")
+                "# layer of bench.py's `roofline` is conv_thin_kernel<2, 1, 1, 4, 2, 1> (CPR, IS3, NB, MT, EPI, TMA) with ~336 MB read\n")
         for r in rows[2:]:
             d = dict(zip(h, r))
             f.write("\n%s\n" % d["Kernel Name"])
             for k in keys:
                 if k in d:
                     f.write("  %-70s %s %s\n" % (k, d[k], rows[1][h.index(k)]))
-            if "conv_thin_kernel<2, 1, 1, 4>" in d["Kernel Name"].replace("(int)", "").replace("(bool)", ""):
+            if "conv_thin_kernel<2, 1, 1, 4," in d["Kernel Name"].replace("(int)", "").replace("(bool)", ""):
                 rd, wr = float(d["dram__bytes_read.sum"]), float(d["dram__bytes_write.sum"])
                 ur, uw = rows[1][h.index("dram__bytes_read.sum")], rows[1][h.index("dram__bytes_write.sum")]
                 mul = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
                 tot = rd * mul[ur] + wr * mul[uw]
                 if best is None or rd * mul[ur] > best[1]:
-                    best = (tot, rd * mul[ur], float(d["gpu__time_duration.sum"]))
+                    best = (tot, rd * mul[ur], float(d["gpu__time_duration.sum"]), rows.index(r) - 2, d["Kernel Name"])
     if best:
         with open(os.path.join(P, "top_kernel_traffic.json"), "w") as f:
-            json.dump({"kernel": "thin::conv_thin_kernel<2,1,1,4> 16->16 3x3 @256x256, n=160 (+BN/ReLU prologue, stats epilogue)",
+            json.dump({"kernel": "thin::%s 16->16 3x3 @256x256, n=160 (+BN/ReLU prologue, stats epilogue)" % best[4].replace("(Params, CUtensorMap_st)", ""),
                        "dram_bytes_per_launch": best[0], "ncu_duration_us": best[2],
                        "source": "profiles/ncu_top_kernel_%s.txt (dram__bytes_read.sum + dram__bytes_write.sum)" % R}, f)
             f.write("\n")
-    st = run(sys.executable, "tools/ncu_stalls.py", rep, "9", "30")
+    st = run(sys.executable, "tools/ncu_stalls.py", rep, str(best[3] if best else 9), "30")
     with open(os.path.join(P, "ncu_top_kernel_%s_stalls.txt" % R), "w") as f:
-        f.write("# python tools/ncu_stalls.py gpurun_out/prof_thin.ncu-rep 9 30 : warp-state samples per SASS line of the roofline launch\n" + st)
+        f.write("# python tools/ncu_stalls.py gpurun_out/prof_thin.ncu-rep <launch> 30 : warp-state samples per SASS line of the roofline launch\n" + st)
 print(sorted(os.listdir(P)))
