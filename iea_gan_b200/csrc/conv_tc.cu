@@ -113,6 +113,78 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
         }
       }
       const int cc = pt % CPR;  // chunk handled by this thread (e % CPR is the same for every i)
+      // ---- software-pipelined path (same-resolution / nearest-up2 inputs): the raw 16-byte chunks of step
+      // it+1 are requested BEFORE step it is transformed and stored, so a step no longer pays a full global
+      // load round trip (these 4x4..16x16 layers are pure latency: 18 steps per tile, 2 tiles per CTA)
+      if (d.in_mode != IEA_IN_POOL2) {
+        const bool affine = d.in_scale != nullptr, relu = d.in_relu != 0;
+        const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
+        const bf16* xb = (const bf16*)d.x;
+        uint4 nxt[CPR];
+        uint32_t nxt_ok = 0;
+        auto raw_load = [&](int it) {
+          const int tap = it / p.nkb, kb = it - tap * p.nkb;
+          int dh = 0, dw = 0;
+          if (d.ksize == 3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+          const int ci = kb * p.KB + cc * 8;
+          nxt_ok = 0;
+#pragma unroll
+          for (int i = 0; i < CPR; ++i) {
+            const int ih = oh_[i] + dh, iw = ow_[i] + dw;
+            if ((unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w) {
+              nxt[i] = __ldg(reinterpret_cast<const uint4*>(xb + ((n_[i] * p.hs + (ih >> sh_)) * (int64_t)p.ws + (iw >> sh_)) * d.x_ld + ci));
+              nxt_ok |= 1u << i;
+            }
+          }
+        };
+        raw_load(0);
+        for (int it = 0; it < k_iters; ++it, ++g) {
+          const uint32_t s = g % p.stages, ph = (g / p.stages) & 1;
+          const int tap = it / p.nkb, kb = it - tap * p.nkb;
+          uint4 cur[CPR];
+          const uint32_t cur_ok = nxt_ok;
+#pragma unroll
+          for (int i = 0; i < CPR; ++i) cur[i] = nxt[i];
+          if (it + 1 < k_iters) raw_load(it + 1);
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t a0 = sbase + s * p.stage_bytes;
+          if (pt == 0) {
+            mbar_expect_tx(full_bar(s), p.b_bytes);
+#pragma unroll
+            for (int c = 0; c < CPR; ++c)
+              bulk_g2s(a0 + p.a_bytes + c * p.lbo_b,
+                       p.wtc + ((((int64_t)tap * p.nkb + kb) * CPR + c) * d.cout + n0) * 8, p.BN * 16, full_bar(s));
+          }
+          const int ci = kb * p.KB + cc * 8;
+#pragma unroll
+          for (int i = 0; i < CPR; ++i) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (cur_ok >> i & 1) {
+              v = cur[i];
+              if (affine || relu) {
+                float f[8];
+                unpack8(v, f);
+                if (affine) {
+                  const int64_t si = (d.in_bcast ? 0 : n_[i] * d.cin) + ci;
+                  const float4 s0 = *reinterpret_cast<const float4*>(d.in_scale + si), s1 = *reinterpret_cast<const float4*>(d.in_scale + si + 4);
+                  const float4 h0 = *reinterpret_cast<const float4*>(d.in_shift + si), h1 = *reinterpret_cast<const float4*>(d.in_shift + si + 4);
+                  f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y); f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
+                  f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y); f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
+                }
+                if (relu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                v = pack8(f);
+              }
+            }
+            *reinterpret_cast<uint4*>(smem + s * p.stage_bytes + cc * p.lbo_a + (r_[i] >> 3) * 128 + (r_[i] & 7) * 16) = v;
+          }
+          fence_async_smem();
+          mbar_arrive(full_bar(s));
+        }
+        continue;
+      }
       for (int it = 0; it < k_iters; ++it, ++g) {
         const uint32_t s = g % p.stages, ph = (g / p.stages) & 1;
         const int tap = it / p.nkb, kb = it - tap * p.nkb;
