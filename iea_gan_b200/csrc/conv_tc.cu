@@ -28,7 +28,9 @@ struct Params {
   int64_t M;
   int hs, ws, KB, nkb, BN, n_tiles_m, n_tiles_n, stages, taps;
   uint32_t a_bytes, b_bytes, lbo_a, lbo_b, stage_bytes, staging_off, staging_ld, bar_off, stat_off, tmem_cols;
+  uint32_t tab_off;  // bf16 scale / shift table of the images of the current tile: [TAB_IMGS][cin] x 2
 };
+constexpr int TAB_IMGS = 8;
 
 
 template <int CPR>
@@ -120,6 +122,34 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
         const bool affine = d.in_scale != nullptr, relu = d.in_relu != 0;
         const int sh_ = d.in_mode == IEA_IN_UP2 ? 1 : 0;
         const bf16* xb = (const bf16*)d.x;
+        // fused-prologue constants of the (<= TAB_IMGS) images this tile touches, as bf16 pairs in shared memory:
+        // the per-chunk transform is then 2 LDS + 4 packed fma.relu (the same rounding as conv_thin / conv_tc2)
+        // instead of four dependent global loads and ~40 fp32 instructions per 16-byte chunk
+        const int hw_ = d.h * d.w;
+        const int64_t img0 = m0 / hw_;
+        int64_t img1 = (m0 + BM - 1 < p.M ? m0 + BM - 1 : p.M - 1) / hw_;
+        const int nimg = d.in_bcast ? 1 : (int)(img1 - img0 + 1);
+        const bool tab = affine && nimg <= TAB_IMGS;
+        bf16* const tsc = reinterpret_cast<bf16*>(smem + p.tab_off);
+        bf16* const tsh = tsc + TAB_IMGS * d.cin;
+        if (affine) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");  // every producer is done with the previous tile's table
+          if (tab) {
+            const int c8n = d.cin >> 3;
+            for (int e = pt; e < nimg * c8n; e += 128) {
+              const int li = e / c8n, c8 = e - li * c8n;
+              const int64_t si = (d.in_bcast ? 0 : (img0 + li) * d.cin) + c8 * 8;
+              float a[8], b[8];
+              *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(d.in_scale + si);
+              *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(d.in_scale + si + 4);
+              *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(d.in_shift + si);
+              *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(d.in_shift + si + 4);
+              *reinterpret_cast<uint4*>(tsc + li * d.cin + c8 * 8) = pack8(a);
+              *reinterpret_cast<uint4*>(tsh + li * d.cin + c8 * 8) = pack8(b);
+            }
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
         uint4 nxt[CPR];
         uint32_t nxt_ok = 0;
         auto raw_load = [&](int it) {
@@ -161,7 +191,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
             uint4 v = make_uint4(0, 0, 0, 0);
             if (cur_ok >> i & 1) {
               v = cur[i];
-              if (affine || relu) {
+              if (tab) {
+                const int li = d.in_bcast ? 0 : (int)(n_[i] - img0);
+                const uint4 s4 = *reinterpret_cast<const uint4*>(tsc + li * d.cin + ci), h4 = *reinterpret_cast<const uint4*>(tsh + li * d.cin + ci);
+                __nv_bfloat162* x2 = reinterpret_cast<__nv_bfloat162*>(&v);
+                const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&s4);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&h4);
+                if (relu) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) x2[j] = __hfma2_relu(x2[j], s2[j], h2[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) x2[j] = __hfma2(x2[j], s2[j], h2[j]);
+                }
+              } else if (affine || relu) {
                 float f[8];
                 unpack8(v, f);
                 if (affine) {
@@ -395,14 +438,16 @@ int iea_conv_fprop_tc(const iea_conv_desc* d, cudaStream_t s) {
   p.staging_ld = p.BN * 2 + 16;
   const uint32_t staging_bytes = (tc::BM * p.staging_ld + 127) / 128 * 128;
   const uint32_t stat_bytes = 1024 * 2 * 4 > p.BN * 2 * 4 ? 1024 * 2 * 4 : p.BN * 2 * 4;
-  const uint32_t fixed = staging_bytes + stat_bytes + 256;
+  const uint32_t tab_bytes = d->in_scale ? (uint32_t)(tc::TAB_IMGS * d->cin * 2 * 2) : 0;
+  const uint32_t fixed = staging_bytes + stat_bytes + tab_bytes + 256;
   int stages = (int)((200 * 1024 - fixed) / p.stage_bytes);
   if (stages > 6) stages = 6;
   IEA_CHECK_ARG(stages >= 2, "iea_conv_fprop(tcgen05): tile does not fit shared memory (cin=%d cout=%d)", d->cin, d->cout);
   p.stages = stages;
   p.staging_off = stages * p.stage_bytes;
   p.stat_off = p.staging_off + staging_bytes;
-  p.bar_off = p.stat_off + stat_bytes;
+  p.tab_off = p.stat_off + stat_bytes;
+  p.bar_off = p.tab_off + tab_bytes;
   const uint32_t smem = p.bar_off + 256;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.BN)) cols <<= 1;
