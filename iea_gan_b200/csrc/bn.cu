@@ -186,26 +186,54 @@ __global__ void __launch_bounds__(256) bn_finalize_fused_kernel(const float* par
                                                                 float eps, float* mean_io, float* rstd_io, float* scale,
                                                                 float* shift) {
   __shared__ double r1[256], r2[256];
+  __shared__ float mean_s[8], rstd_s[8];
   __shared__ bool last;
   const int e = blockIdx.x, cl = threadIdx.x & 7, tl = threadIdx.x >> 3, cc = blockIdx.y * 8 + cl;
   double s1 = 0.0, s2 = 0.0;
   if (cc < c) {
     const float* p = partials + ((int64_t)e * tiles * c + cc) * 2;
-    for (int t = tl; t < tiles; t += 32) {
+    int t = tl;
+    for (; t + 96 < tiles; t += 128) {  // four independent loads in flight
+      const float2 v0 = *reinterpret_cast<const float2*>(p + (int64_t)t * c * 2);
+      const float2 v1 = *reinterpret_cast<const float2*>(p + (int64_t)(t + 32) * c * 2);
+      const float2 v2 = *reinterpret_cast<const float2*>(p + (int64_t)(t + 64) * c * 2);
+      const float2 v3 = *reinterpret_cast<const float2*>(p + (int64_t)(t + 96) * c * 2);
+      s1 += (double)v0.x; s2 += (double)v0.y; s1 += (double)v1.x; s2 += (double)v1.y;
+      s1 += (double)v2.x; s2 += (double)v2.y; s1 += (double)v3.x; s2 += (double)v3.y;
+    }
+    for (; t < tiles; t += 32) {
       const float2 v = *reinterpret_cast<const float2*>(p + (int64_t)t * c * 2);
       s1 += (double)v.x; s2 += (double)v.y;
     }
   }
   r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
   __syncthreads();
-  if (tl == 0 && cc < c) {
-    double a = 0.0, b = 0.0;
-    for (int l = 0; l < 32; ++l) { a += r1[l * 8 + cl]; b += r2[l * 8 + cl]; }
-    const double m = a / count;
-    double var = b / count - m * m;
-    if (var < 0.0) var = 0.0;
-    mean_io[e * c + cc] = (float)m;
-    rstd_io[e * c + cc] = (float)var;  // variance until the last block converts it
+  if (tl == 0) {
+    float mu = 0.f, rs = 0.f;
+    if (cc < c) {
+      double a = 0.0, b = 0.0;
+      for (int l = 0; l < 32; ++l) { a += r1[l * 8 + cl]; b += r2[l * 8 + cl]; }
+      const double m = a / count;
+      double var = b / count - m * m;
+      if (var < 0.0) var = 0.0;
+      mu = (float)m;
+      rs = (float)(1.0 / sqrt((double)(float)var + (double)eps));  // (from the fp32-rounded variance, like the fold below)
+      mean_io[e * c + cc] = mu;
+      rstd_io[e * c + cc] = (float)var;  // variance until the last block of the channel group converts it
+    }
+    mean_s[cl] = mu; rstd_s[cl] = rs;
+  }
+  __syncthreads();
+  // this event's per-image scale / shift for the 8 channels: needs nothing from the other events
+  for (int i = threadIdx.x; i < imgs * 8; i += 256) {
+    const int ch = blockIdx.y * 8 + (i & 7);
+    if (ch >= c) continue;
+    const int64_t n = (int64_t)e * imgs + (i >> 3);
+    const float gn = gain_add + (gain ? gain[n * gain_ld + ch] : 0.f);
+    const float bs = bias ? bias[n * bias_ld + ch] : 0.f;
+    const float sc = rstd_s[i & 7] * gn;
+    scale[n * c + ch] = sc;
+    shift[n * c + ch] = bs - mean_s[i & 7] * sc;
   }
   __threadfence();
   __syncthreads();
@@ -217,10 +245,7 @@ __global__ void __launch_bounds__(256) bn_finalize_fused_kernel(const float* par
   __syncthreads();
   if (!last) return;
   __threadfence();
-  // (everything below runs in ONE block per channel group: keep it off the memory-latency chain -- the
-  //  per-event statistics are staged in shared memory by all threads first, the sequential running-statistics
-  //  recursion then reads shared memory only)
-  __shared__ float rs_s[512];                   // [events][8] rstd
+  // last block of this channel group: running statistics in event order, variance -> rstd for the backward pass
   float* m_s = reinterpret_cast<float*>(r1);    // [events][8] mean      (events <= 64)
   float* v_s = reinterpret_cast<float*>(r2);    // [events][8] biased variance
   for (int i = threadIdx.x; i < events * 8; i += 256) {
@@ -228,7 +253,6 @@ __global__ void __launch_bounds__(256) bn_finalize_fused_kernel(const float* par
     float mu = 0.f, var = 0.f;
     if (ch < c) { mu = __ldcg(mean_io + ev * c + ch); var = __ldcg(rstd_io + ev * c + ch); }
     m_s[i] = mu; v_s[i] = var;
-    rs_s[i] = (float)(1.0 / sqrt((double)var + (double)eps));
   }
   __syncthreads();
   if (tl == 0 && cc < c) {
@@ -243,21 +267,7 @@ __global__ void __launch_bounds__(256) bn_finalize_fused_kernel(const float* par
   }
   for (int i = threadIdx.x; i < events * 8; i += 256) {
     const int ev = i >> 3, ch = blockIdx.y * 8 + (i & 7);
-    if (ch < c) rstd_io[ev * c + ch] = rs_s[i];
-  }
-  const int64_t nimg = (int64_t)events * imgs;
-#pragma unroll 4
-  for (int64_t i = threadIdx.x; i < nimg * 8; i += 256) {
-    const int64_t n = i >> 3;
-    const int ch = blockIdx.y * 8 + (int)(i & 7);
-    if (ch >= c) continue;
-    const int ev = (int)(n / imgs);
-    const float rstd = rs_s[ev * 8 + (i & 7)], mean = m_s[ev * 8 + (i & 7)];
-    const float gn = gain_add + (gain ? gain[n * gain_ld + ch] : 0.f);
-    const float bs = bias ? bias[n * bias_ld + ch] : 0.f;
-    const float sc = rstd * gn;
-    scale[n * c + ch] = sc;
-    shift[n * c + ch] = bs - mean * sc;
+    if (ch < c) rstd_io[ev * c + ch] = (float)(1.0 / sqrt((double)v_s[i] + (double)eps));
   }
 }
 }  // namespace
