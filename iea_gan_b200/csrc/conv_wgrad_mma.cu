@@ -340,10 +340,10 @@ struct P3 {
   FastDiv fd_mtw, fd_mth;
 };
 
-template <int CPA, int CPG, int MT>
+template <int CPA, int CPG, int MT, bool IS3 = true>
 struct G3 {
   static constexpr int PWM = 8 * MT + 2;
-  static constexpr int NPA = PH * PWM;                 // patch pixels
+  static constexpr int NPA = IS3 ? PH * PWM : 128 * MT;  // staged input pixels (3x3: halo patch; 1x1: the pixel run)
   static constexpr int NPG = 128 * MT;                 // g rows
   static constexpr int NSA = (NPA * CPA + 255) / 256;  // chunk slots per thread
   static constexpr int NSG = NPG * CPG / 256;
@@ -353,10 +353,10 @@ struct G3 {
   static constexpr uint32_t STAGE = (GOFF + CPG * PLG + 127) / 128 * 128;
 };
 
-template <int CPA, int CPG, int MT>
+template <int CPA, int CPG, int MT, bool IS3>
 __global__ void __launch_bounds__(256) wgrad3_kernel(const P3 p) {
-  using G = G3<CPA, CPG, MT>;
-  constexpr int PWM = G::PWM, NSA = G::NSA, NSG = G::NSG;
+  using G = G3<CPA, CPG, MT, IS3>;
+  constexpr int PWM = G::PWM, NSA = G::NSA, NSG = G::NSG, TAPS = IS3 ? 9 : 1;
   constexpr int NIB = CPA / 2, NCB = CPG / 2, P = NIB * NCB, WP = 8 / P, KS = 8 * MT;
   extern __shared__ __align__(128) uint8_t smem[];
   const iea_conv_desc& d = p.d;
@@ -376,24 +376,32 @@ __global__ void __launch_bounds__(256) wgrad3_kernel(const P3 p) {
   for (int i = 0; i < NSA; ++i) {
     const int q = tid + 256 * i, pp = q / CPA;
     if (q < G::NPA * CPA) m_valid |= 1u << i;
-    const int pi = pp / PWM, pj = pp - pi * PWM;
-    goa[i] = (((pi - 1) >> sh_) * p.ws + ((pj - 1) >> sh_)) * d.x_ld + ca * 8;
     soa[i] = ca * G::PLA + pp * 16;
-    if (pi == 0) m_top |= 1u << i;
-    if (pi == PH - 1) m_bot |= 1u << i;
-    if (pj == 0) m_left |= 1u << i;
-    if (pj == PWM - 1) m_right |= 1u << i;
+    if (IS3) {
+      const int pi = pp / PWM, pj = pp - pi * PWM;
+      goa[i] = (((pi - 1) >> sh_) * p.ws + ((pj - 1) >> sh_)) * d.x_ld + ca * 8;
+      if (pi == 0) m_top |= 1u << i;
+      if (pi == PH - 1) m_bot |= 1u << i;
+      if (pj == 0) m_left |= 1u << i;
+      if (pj == PWM - 1) m_right |= 1u << i;
+    } else {
+      goa[i] = pp * d.x_ld + ca * 8;
+    }
   }
 #pragma unroll
   for (int i = 0; i < NSG; ++i) {
     const int q = tid + 256 * i, r = q / CPG;            // r = sb*128 + (row*8 + col) inside the sub-tile
     const int sb = r >> 7, lr = r & 127;
-    gog[i] = ((lr >> 3) * d.w + sb * 8 + (lr & 7)) * p.g_ld + cg * 8;
+    gog[i] = IS3 ? ((lr >> 3) * d.w + sb * 8 + (lr & 7)) * p.g_ld + cg * 8 : r * p.g_ld + cg * 8;
     sog[i] = G::GOFF + cg * G::PLG + r * 16;
   }
   struct Pos { int n, th, tw; };
   auto pos_of = [&](int item) {
     Pos c;
+    if (!IS3) {  // mtw = macro tiles per image: n = item / mtw
+      c.n = (int)fdiv((unsigned)item, p.fd_mtw); c.th = 0; c.tw = item;
+      return c;
+    }
     const unsigned t = fdiv((unsigned)item, p.fd_mtw);
     c.tw = (int)((unsigned)item - t * (unsigned)p.mtw);
     c.n = (int)fdiv(t, p.fd_mth);
@@ -401,6 +409,7 @@ __global__ void __launch_bounds__(256) wgrad3_kernel(const P3 p) {
     return c;
   };
   auto pad_of = [&](const Pos& c) -> uint32_t {
+    if (!IS3) return 0u;
     return (c.th == 0 ? m_top : 0u) | (c.th == p.mth - 1 ? m_bot : 0u) | (c.tw == 0 ? m_left : 0u) |
            (c.tw == p.mtw - 1 ? m_right : 0u);
   };
@@ -408,8 +417,10 @@ __global__ void __launch_bounds__(256) wgrad3_kernel(const P3 p) {
   auto issue = [&](int it) {
     const Pos c = pos_of((int)blockIdx.x + it * (int)gridDim.x);
     const uint32_t s0 = sbase + (uint32_t)(it % p.stages) * G::STAGE;
-    const bf16* ap = xb + ((int64_t)(c.n * p.hs + ((c.th * 16) >> sh_)) * p.ws + ((c.tw * (8 * MT)) >> sh_)) * d.x_ld;
-    const bf16* gp = p.g + ((int64_t)(c.n * d.h + c.th * 16) * d.w + c.tw * (8 * MT)) * p.g_ld;
+    const bf16* ap = IS3 ? xb + ((int64_t)(c.n * p.hs + ((c.th * 16) >> sh_)) * p.ws + ((c.tw * (8 * MT)) >> sh_)) * d.x_ld
+                         : xb + (int64_t)c.tw * (128 * MT) * d.x_ld;
+    const bf16* gp = IS3 ? p.g + ((int64_t)(c.n * d.h + c.th * 16) * d.w + c.tw * (8 * MT)) * p.g_ld
+                         : p.g + (int64_t)c.tw * (128 * MT) * p.g_ld;
     const uint32_t pad = pad_of(c);
 #pragma unroll
     for (int i = 0; i < NSA; ++i) {
@@ -425,9 +436,9 @@ __global__ void __launch_bounds__(256) wgrad3_kernel(const P3 p) {
   const int pair = warp % P, kg = warp / P;
   const int cb = pair / NIB, ib = pair - cb * NIB;
   const bool cs_on = p.cs_parts != nullptr && ib == 0;
-  float acc[9][2][4], acc_cs[4];
+  float acc[TAPS][2][4], acc_cs[4];
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < TAPS; ++t)
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -489,11 +500,12 @@ __global__ void __launch_bounds__(256) wgrad3_kernel(const P3 p) {
       uint32_t a[4];
       ldsm_x4_t(s0 + G::GOFF + (cb * 2 + (mat & 1)) * G::PLG + (sb * 128 + kl * 16 + (mat >> 1) * 8 + rr) * 16, a[0], a[1], a[2], a[3]);
       if (cs_on) mma16816(acc_cs, a, 0x3F803F80u, 0x3F803F80u);
-      const uint32_t brow = s0 + (ib * 2 + (mat >> 1)) * G::PLA + (uint32_t)((2 * kl + (mat & 1)) * PWM + sb * 8 + rr) * 16;
+      const uint32_t brow = s0 + (ib * 2 + (mat >> 1)) * G::PLA +
+                            (uint32_t)(IS3 ? (2 * kl + (mat & 1)) * PWM + sb * 8 + rr : ks * 16 + (mat & 1) * 8 + rr) * 16;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
+      for (int t = 0; t < TAPS; ++t) {
         uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(brow + (uint32_t)((t / 3) * PWM + t % 3) * 16, b0, b1, b2, b3);
+        ldsm_x4_t(brow + (uint32_t)(IS3 ? (t / 3) * PWM + t % 3 : 0) * 16, b0, b1, b2, b3);
         mma16816(acc[t][0], a, b0, b1);
         mma16816(acc[t][1], a, b2, b3);
       }
@@ -503,44 +515,45 @@ __global__ void __launch_bounds__(256) wgrad3_kernel(const P3 p) {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   // ---- fold the k-step groups (fixed order), then one partial per CTA: gpart[blockIdx.x][cout][9][cin]
   if (WP > 1) {
-    float* scr = reinterpret_cast<float*>(smem);  // [P][76][32]
+    float* scr = reinterpret_cast<float*>(smem);  // [P][TAPS*8 + 4][32]
+    constexpr int FS = TAPS * 8 + 4;
     __syncthreads();
     for (int kgi = 1; kgi < WP; ++kgi) {
       if (kg == kgi) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
+        for (int t = 0; t < TAPS; ++t)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) scr[(pair * 76 + t * 8 + j * 4 + r) * 32 + lane] = acc[t][j][r];
+            for (int r = 0; r < 4; ++r) scr[(pair * FS + t * 8 + j * 4 + r) * 32 + lane] = acc[t][j][r];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) scr[(pair * 76 + 72 + r) * 32 + lane] = acc_cs[r];
+        for (int r = 0; r < 4; ++r) scr[(pair * FS + TAPS * 8 + r) * 32 + lane] = acc_cs[r];
       }
       __syncthreads();
       if (kg == 0) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
+        for (int t = 0; t < TAPS; ++t)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[t][j][r] += scr[(pair * 76 + t * 8 + j * 4 + r) * 32 + lane];
+            for (int r = 0; r < 4; ++r) acc[t][j][r] += scr[(pair * FS + t * 8 + j * 4 + r) * 32 + lane];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc_cs[r] += scr[(pair * 76 + 72 + r) * 32 + lane];
+        for (int r = 0; r < 4; ++r) acc_cs[r] += scr[(pair * FS + TAPS * 8 + r) * 32 + lane];
       }
       __syncthreads();
     }
   }
   if (kg != 0) return;
-  float* out = p.gpart + (int64_t)blockIdx.x * d.cout * 9 * d.cin;
+  float* out = p.gpart + (int64_t)blockIdx.x * d.cout * TAPS * d.cin;
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < TAPS; ++t)
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int co = cb * 16 + (lane >> 2) + (r >= 2 ? 8 : 0);
         const int ci = ib * 16 + j * 8 + 2 * (lane & 3) + (r & 1);
-        out[((int64_t)co * 9 + t) * d.cin + ci] = acc[t][j][r];
+        out[((int64_t)co * TAPS + t) * d.cin + ci] = acc[t][j][r];
       }
   if (cs_on && (lane & 3) == 0) {
     const int co = cb * 16 + (lane >> 2);
@@ -625,30 +638,44 @@ int iea_conv_c1_wgrad(const iea_conv_desc* d, const void* g, int g_dtype, int g_
 // macro-tile kernel: 0 = shape not handled, else MT (sub-tiles per macro tile)
 static int wgrad3_mt(const iea_conv_desc* d, int g_dtype, int g_ld) {
   { const char* e_ = getenv("IEA_WGRAD3"); if (e_ && e_[0] == '0') return 0; }  // test / profiling switch: generic mma kernel
-  if (d->ksize != 3 || (d->cin != 16 && d->cin != 32) || (d->cout != 16 && d->cout != 32)) return 0;
+  const bool is3 = d->ksize == 3;
+  if (is3) {
+    if ((d->cin != 16 && d->cin != 32) || (d->cout != 16 && d->cout != 32)) return 0;
+  } else {
+    if ((d->cin != 16 && d->cin != 32 && d->cin != 64) || (d->cout != 16 && d->cout != 32 && d->cout != 64)) return 0;
+    if (d->cin * d->cout > 64 * 32 || d->in_mode != IEA_IN_DIRECT) return 0;  // <= 8 (16x16) block pairs: one per warp
+  }
   if (d->in_mode == IEA_IN_POOL2 || d->x_dtype != IEA_BF16 || g_dtype != IEA_BF16) return 0;
   if (d->x_ld % 8 || g_ld % 8 || (reinterpret_cast<uintptr_t>(d->x) & 15)) return 0;
-  if (d->h % 16 || d->w % 16) return 0;
+  if (is3 && (d->h % 16 || d->w % 16)) return 0;
   if (d->in_scale && ((reinterpret_cast<uintptr_t>(d->in_scale) & 15) || (reinterpret_cast<uintptr_t>(d->in_shift) & 15))) return 0;
   const int64_t M = d->n * (int64_t)d->h * d->w;
   if (M >= (1ll << 31) || M * (int64_t)(d->x_ld > g_ld ? d->x_ld : g_ld) >= (1ll << 31) || M < 8192) return 0;
+  if (!is3) {  // 1x1: runs of 128*mt pixels inside one image; three stages must fit next to a second CTA
+    const int planes = (d->cin + d->cout) / 8;
+    int mt = planes <= 4 ? 4 : (planes <= 8 ? 2 : 1);
+    const int64_t hw = (int64_t)d->h * d->w;
+    while (mt > 1 && hw % (128 * mt)) mt >>= 1;
+    return hw % (128 * mt) == 0 ? mt : 0;
+  }
   int mt = (d->cin == 16 && d->cout == 16) ? 4 : 2;
   while (mt > 1 && d->w % (8 * mt)) mt >>= 1;
   return mt >= 2 ? mt : 0;
 }
-template <int CPA, int CPG, int MT>
+template <int CPA, int CPG, int MT, bool IS3>
 static int wgrad3_setup(const iea_conv_desc* d, wg::P3& p, int& grid, uint32_t& smem) {
-  using G = wg::G3<CPA, CPG, MT>;
+  using G = wg::G3<CPA, CPG, MT, IS3>;
   p.d = *d;
   p.hs = d->in_mode == IEA_IN_UP2 ? d->h / 2 : d->h;
   p.ws = d->in_mode == IEA_IN_UP2 ? d->w / 2 : d->w;
-  p.mtw = d->w / (8 * MT); p.mth = d->h / 16;
+  if (IS3) { p.mtw = d->w / (8 * MT); p.mth = d->h / 16; }
+  else { p.mtw = (int)(((int64_t)d->h * d->w) / (128 * MT)); p.mth = 1; }  // macro tiles per image
   p.n_macro = (int)(d->n * (int64_t)p.mtw * p.mth);
   p.fd_mtw = wg::make_fastdiv(p.mtw); p.fd_mth = wg::make_fastdiv(p.mth);
   p.stages = 3; p.depth = 3;
   if (p.stages * G::STAGE > 110 * 1024) { p.stages = 2; p.depth = 2; }
   smem = p.stages * G::STAGE;
-  constexpr uint32_t fold = (uint32_t)((CPA / 2) * (CPG / 2)) * 76 * 32 * 4;
+  constexpr uint32_t fold = (uint32_t)((CPA / 2) * (CPG / 2)) * ((IS3 ? 72 : 8) + 4) * 32 * 4;
   if (smem < fold) smem = fold;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -663,18 +690,22 @@ static int wgrad3_run(const iea_conv_desc* d, const void* g, int g_dtype, int g_
   if (!mt) return 0;
   wg::P3 p; int grid = 0; uint32_t smem = 0;
   const int cpa = d->cin / 8, cpg = d->cout / 8;
+  const bool is3 = d->ksize == 3;
   p.g = (const bf16*)g; p.g_ld = g_ld; p.gpart = parts; p.cs_parts = cs_parts;
-#define IEA_W3(A_, G_, M_)                                                                                      \
-  if (cpa == A_ && cpg == G_ && mt == M_) {                                                                       \
-    wgrad3_setup<A_, G_, M_>(d, p, grid, smem);                                                                    \
+#define IEA_W3(A_, G_, M_, I_)                                                                                     \
+  if (cpa == A_ && cpg == G_ && mt == M_ && is3 == I_) {                                                                     \
+    wgrad3_setup<A_, G_, M_, I_>(d, p, grid, smem);                                                                 \
     if (parts) {                                                                                                  \
-      auto kern = wg::wgrad3_kernel<A_, G_, M_>;                                                                   \
+      auto kern = wg::wgrad3_kernel<A_, G_, M_, I_>;                                                                \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1; \
       kern<<<grid, 256, smem, s>>>(p);                                                                            \
     }                                                                                                             \
     return grid;                                                                                                  \
   }
-  IEA_W3(2, 2, 4) IEA_W3(2, 2, 2) IEA_W3(2, 4, 2) IEA_W3(4, 2, 2) IEA_W3(4, 4, 2)
+  IEA_W3(2, 2, 4, true) IEA_W3(2, 2, 2, true) IEA_W3(2, 4, 2, true) IEA_W3(4, 2, 2, true) IEA_W3(4, 4, 2, true)
+  IEA_W3(2, 2, 4, false) IEA_W3(2, 2, 2, false) IEA_W3(2, 2, 1, false) IEA_W3(2, 4, 2, false) IEA_W3(2, 4, 1, false)
+  IEA_W3(4, 2, 2, false) IEA_W3(4, 2, 1, false) IEA_W3(4, 4, 2, false) IEA_W3(4, 4, 1, false) IEA_W3(2, 8, 1, false)
+  IEA_W3(8, 2, 1, false) IEA_W3(4, 8, 1, false) IEA_W3(8, 4, 1, false)
 #undef IEA_W3
   return 0;
 }
@@ -682,7 +713,7 @@ static int wgrad3_run(const iea_conv_desc* d, const void* g, int g_dtype, int g_
 extern "C" int iea_conv_wgrad_mma_slices(const iea_conv_desc* d, int g_dtype, int g_ld) {
   if (const int c1g = iea_conv_c1_wgrad_grid(d, g_dtype, g_ld)) return c1g + 1;  // 1-channel side: conv_c1.cu
   if (const int g3 = wgrad3_run(d, nullptr, g_dtype, g_ld, nullptr, nullptr, nullptr)) {
-    const int64_t total = (int64_t)d->cout * 9 * d->cin;
+    const int64_t total = (int64_t)d->cout * d->ksize * d->ksize * d->cin;
     return g3 + 1 + (int)(((int64_t)g3 * d->cout + total - 1) / total);
   }
   wg::Params p; int npair;
@@ -709,7 +740,7 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
     return check_launch("iea_conv_wgrad_mma(1-channel)");  // 0: the bias gradient was not produced
   }
   if (const int g3 = wgrad3_run(d, nullptr, g_dtype, g_ld, nullptr, nullptr, nullptr)) {  // macro-tile kernel
-    const int64_t total = (int64_t)d->cout * 9 * d->cin;
+    const int64_t total = (int64_t)d->cout * d->ksize * d->ksize * d->cin;
     float* parts = gpart + total;
     float* csp = dbias ? gpart + (int64_t)(g3 + 1) * total : nullptr;
     const int rc3 = wgrad3_run(d, g, g_dtype, g_ld, parts, csp, (cudaStream_t)stream);

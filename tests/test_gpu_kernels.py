@@ -324,7 +324,10 @@ def _tc_vs_generic(eng, variant, cin, cout, k, mode, relu, aff, resm, hw, n):
                                               (32, 16, 3, (12, 20), "bf16"),
                                               # macro-tile kernel (Cin, Cout in {16, 32}; 4- and 2-wide macro tiles)
                                               (16, 16, 3, (32, 64), "bf16"), (32, 32, 3, (16, 32), "bf16"),
-                                              (16, 32, 3, (32, 16), "bf16"), (32, 16, 3, (16, 16), "bf16")])
+                                              (16, 32, 3, (32, 16), "bf16"), (32, 16, 3, (16, 16), "bf16"),
+                                              # ... and its 1x1 form (pixel runs of 128*mt inside an image)
+                                              (32, 16, 1, (32, 32), "bf16"), (64, 32, 1, (16, 16), "bf16"),
+                                              (16, 64, 1, (16, 32), "bf16"), (16, 16, 1, (32, 32), "bf16")])
 def test_wgrad_mma_thin_and_wide(eng, cin, cout, k, hw, gdt):
     """The 1-channel stem / output convs (zero-extended operands) and the many-block 1x1 shapes of the
     tensor-core weight-gradient kernel against the CUDA-core kernel."""
