@@ -47,8 +47,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.bar_off + 8 * (2 * p.stages + 4));
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 129); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    // one arrival per producer WARP (+1: the expect_tx of the weight copy) -- 128 per-thread arrivals on one
+    // mbarrier serialise and wake the parked MMA thread 128 times per step
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -224,7 +226,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
             *reinterpret_cast<uint4*>(smem + s * p.stage_bytes + cc * p.lbo_a + (r_[i] >> 3) * 128 + (r_[i] & 7) * 16) = v;
           }
           fence_async_smem();
-          mbar_arrive(full_bar(s));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(s));
         }
         continue;
       }
@@ -249,7 +252,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
           *reinterpret_cast<uint4*>(smem + s * p.stage_bytes + cc * p.lbo_a + (r_[i] >> 3) * 128 + (r_[i] & 7) * 16) = v;
         }
         fence_async_smem();
-        mbar_arrive(full_bar(s));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(s));
       }
     }
   } else {
@@ -329,7 +333,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
         dst[1] = pack8(v + 8);
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(ab));  // accumulator drained: the MMA warp may start the next tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(ab));  // accumulator drained: the MMA warp may start the next tile
       bar_sync_epi();
       // coalesced 16-byte stores of the bf16 tile
       const int cg = p.BN / 8;

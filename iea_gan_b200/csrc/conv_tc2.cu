@@ -163,8 +163,9 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.bar_off + 8 * (2 * p.stages + 5));
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    // one arrival per WARP on full / tempty (128 per-thread arrivals on one mbarrier serialise)
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -412,7 +413,8 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
       }
       if (pt == 0) TRACE(1, it);
       fence_async_smem();
-      mbar_arrive(full_bar(c.s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(c.s));
       if (pt == 0) TRACE(2, it);
       cur_next(ct_);
     }
@@ -566,7 +568,8 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
           }  // valid
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(ab));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(ab));
         if (et == 0) TRACE(7, tcount);
       }
       if (has_stats && my_tiles > 0) flush(ev);
@@ -656,7 +659,8 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
           *reinterpret_cast<uint4*>(srow + cb * 32 + 16) = o1;
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(ab));  // accumulator drained: the MMA warp may start the next tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(ab));  // accumulator drained: the MMA warp may start the next tile
         bar_sync_epi();
         // coalesced copy-out: this thread moves chunk g8 of rows r0, r0 + step, ... (cg rows) -- rows of the tile
         // are contiguous pixel runs in NHWC -- and sums its chunks for the batch-norm statistics on the way
@@ -828,7 +832,8 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
         dst[1] = pack8(v + 8);
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(ab));  // accumulator drained: the MMA warp may start the next tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(ab));  // accumulator drained: the MMA warp may start the next tile
       if (d.cout < 16) continue;
       bar_sync_epi();
       // coalesced 16-byte stores: rows of the tile are contiguous runs of pixels in NHWC
