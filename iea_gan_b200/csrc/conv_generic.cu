@@ -465,6 +465,67 @@ __global__ void __launch_bounds__(256) conv_input_bwd_vec(const iea_conv_desc d,
     }
   }
 }
+// ---- the common case without batch-norm constants (every discriminator layer, and the gradient that flows through
+// D in the generator step): dx = [0.25 *] da * 1[x > 0], same resolution or 2x2 average-pool adjoint.  The mask and the
+// power-of-two scale are exact in packed bf16, so the kernel is 2 loads, ~10 packed instructions and 1 store per
+// 16-byte chunk instead of ~90 fp32 instructions (the general kernel above is instruction-, not bandwidth-bound).
+template <bool POOL, bool RELU, bool ACC>
+__global__ void __launch_bounds__(256) conv_input_bwd_plain(const bf16* __restrict__ x, int x_ld, const bf16* __restrict__ da,
+                                                            bf16* __restrict__ dx, int dx_ld, int cin, int hs, int ws,
+                                                            int ws_sh, int px_per_chunk) {
+  const int64_t n = blockIdx.y;
+  const int cgs = cin >> 3, lanes = 256 / cgs;
+  const int cgi = threadIdx.x % cgs, pl = threadIdx.x / cgs, c0 = cgi * 8;
+  if (pl >= lanes) return;
+  const int npx = hs * ws;
+  const int p0 = blockIdx.x * px_per_chunk;
+  int p1 = p0 + px_per_chunk; if (p1 > npx) p1 = npx;
+  const int h = POOL ? hs >> 1 : hs, w = POOL ? ws >> 1 : ws;  // resolution of da
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f), quarter2 = __floats2bfloat162_rn(0.25f, 0.25f);
+  auto da_ptr = [&](int p) -> const bf16* {
+    if (!POOL) return da + (n * npx + p) * cin + c0;
+    const int xh = ws_sh >= 0 ? p >> ws_sh : p / ws, xw = p - xh * ws;
+    return da + ((n * h + (xh >> 1)) * (int64_t)w + (xw >> 1)) * cin + c0;
+  };
+  constexpr int U = 4;
+  for (int pb = p0 + pl; pb < p1; pb += U * lanes) {
+    uint4 xv[U], gv[U], ov[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * lanes;
+      if (p < p1) {
+        if (RELU) xv[u] = __ldg(reinterpret_cast<const uint4*>(x + (n * npx + p) * x_ld + c0));
+        gv[u] = __ldg(reinterpret_cast<const uint4*>(da_ptr(p)));
+        if (ACC) ov[u] = *reinterpret_cast<const uint4*>(dx + (n * npx + p) * dx_ld + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * lanes;
+      if (p >= p1) continue;
+      __nv_bfloat162* g2 = reinterpret_cast<__nv_bfloat162*>(&gv[u]);
+      const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (RELU) g2[j] = __hmul2(g2[j], __hgt2(x2[j], zero2));  // mask: 1.0 / 0.0 per lane
+        if (POOL) g2[j] = __hmul2(g2[j], quarter2);
+      }
+      if (ACC) {  // dx += value, in fp32 and rounded once like the general kernel
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(&gv[u]);
+        const uint32_t* b = reinterpret_cast<const uint32_t*>(&ov[u]);
+        uint32_t* o = reinterpret_cast<uint32_t*>(&gv[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float lo = __uint_as_float(a[j] << 16) + __uint_as_float(b[j] << 16);
+          const float hi = __uint_as_float(a[j] & 0xFFFF0000u) + __uint_as_float(b[j] & 0xFFFF0000u);
+          __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+          o[j] = *reinterpret_cast<uint32_t*>(&t);
+        }
+      }
+      *reinterpret_cast<uint4*>(dx + (n * npx + p) * dx_ld + c0) = gv[u];
+    }
+  }
+}
 __global__ void input_bwd_reduce(const float* part, int64_t n, int chunks, int cin, float* dscale, float* dshift) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * cin) return;
@@ -487,6 +548,26 @@ extern "C" int iea_conv_input_bwd(const iea_conv_desc* d, const void* da, int da
                    d->cin <= 2048 && d->x_ld % 8 == 0 && (!dx || dx_ld % 8 == 0) && scratch != nullptr &&
                    (reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(da) & 15) == 0 &&
                    (!dx || (reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+  if (vec && dx && !d->in_scale && !dscale && d->in_mode != IEA_IN_UP2 && (beta == 0.f || beta == 1.f) &&
+      256 % (d->cin / 8) == 0) {
+    const int npx = g.hs * g.ws;
+    int chunks = npx / 2048;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    const int ppc = (npx + chunks - 1) / chunks;
+    int ws_sh = -1;
+    if ((g.ws & (g.ws - 1)) == 0) { ws_sh = 0; while ((1 << ws_sh) < g.ws) ++ws_sh; }
+    const dim3 grid(chunks, (unsigned)d->n);
+#define IEA_IBP(P_, R_, A_) conv_input_bwd_plain<P_, R_, A_><<<grid, 256, 0, st>>>((const bf16*)d->x, d->x_ld, (const bf16*)da, \
+                                                                              (bf16*)dx, dx_ld, d->cin, g.hs, g.ws, ws_sh, ppc)
+    const bool pool = d->in_mode == IEA_IN_POOL2, relu = d->in_relu != 0, acc = beta != 0.f;
+    if (pool) { if (relu) { if (acc) IEA_IBP(true, true, true); else IEA_IBP(true, true, false); }
+                else      { if (acc) IEA_IBP(true, false, true); else IEA_IBP(true, false, false); } }
+    else      { if (relu) { if (acc) IEA_IBP(false, true, true); else IEA_IBP(false, true, false); }
+                else      { if (acc) IEA_IBP(false, false, true); else IEA_IBP(false, false, false); } }
+#undef IEA_IBP
+    return check_launch("iea_conv_input_bwd(plain)");
+  }
   if (vec) {
     const int npx = g.hs * g.ws;
     int chunks = npx / 2048;
