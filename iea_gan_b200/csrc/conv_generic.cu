@@ -689,8 +689,21 @@ __global__ void residual_bwd_vec(const bf16* g, int g_ld, int64_t n, int h, int 
   const int ws = res_mode == IEA_IN_UP2 ? w / 2 : (res_mode == IEA_IN_POOL2 ? w * 2 : w);
   const int cgs = dres_c >> 3;
   const int64_t total = n * hs * (int64_t)ws * cgs;
+  // (index arithmetic in 32 bits with shifts for the power-of-two extents every layer has: the six 64-bit
+  //  divisions per chunk of the first version cost more than the memory traffic)
+  const bool small = total < (1ll << 31);
+  const int cg_sh = (cgs & (cgs - 1)) == 0 ? 31 - __clz(cgs) : -1;
+  const int ws_sh = (ws & (ws - 1)) == 0 ? 31 - __clz(ws) : -1;
+  const int hs_sh = (hs & (hs - 1)) == 0 ? 31 - __clz(hs) : -1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cgi = (int)(i % cgs); const int64_t p = i / cgs;
+    int cgi; int64_t p;
+    if (small) {
+      const unsigned iu = (unsigned)i;
+      const unsigned pu = cg_sh >= 0 ? iu >> cg_sh : iu / (unsigned)cgs;
+      cgi = (int)(iu - pu * (unsigned)cgs); p = pu;
+    } else {
+      cgi = (int)(i % cgs); p = i / cgs;
+    }
     const int c0 = cgi * 8;
     float v[8];
 #pragma unroll
@@ -699,7 +712,16 @@ __global__ void residual_bwd_vec(const bf16* g, int g_ld, int64_t n, int h, int 
       if (res_mode == IEA_IN_DIRECT) {
         unpack8v(*reinterpret_cast<const uint4*>(g + p * g_ld + c0), v);
       } else {
-        const int xw = (int)(p % ws); const int64_t t = p / ws; const int xh = (int)(t % hs); const int64_t nn = t / hs;
+        int xw, xh; int64_t nn;
+        if (small) {
+          const unsigned pu = (unsigned)p;
+          const unsigned t = ws_sh >= 0 ? pu >> ws_sh : pu / (unsigned)ws;
+          xw = (int)(pu - t * (unsigned)ws);
+          const unsigned nu = hs_sh >= 0 ? t >> hs_sh : t / (unsigned)hs;
+          xh = (int)(t - nu * (unsigned)hs); nn = nu;
+        } else {
+          xw = (int)(p % ws); const int64_t t = p / ws; xh = (int)(t % hs); nn = t / hs;
+        }
         if (res_mode == IEA_IN_UP2) {
 #pragma unroll
           for (int a = 0; a < 2; ++a)

@@ -47,6 +47,7 @@ struct Params {
   float* cs_parts;  // [gridDim.x][cout] column sums of g (bias gradient) or NULL
   int64_t M;
   int n_tiles, tiles_w, tiles_h, hs, ws, cpa, cpg, cpa_sh, cpg_sh, cin_eff, cout_eff, stages, depth, P, WP;
+  int per_px_affine;     // 1x1 layers whose images are not whole 128-pixel tiles: fused-prologue constants per pixel
   int nib_l, ncb_l, gi;  // output split over blockIdx.y: ci blocks / co blocks per CTA, groups along ci
   uint32_t plane_a, plane_g, stage_bytes, g_off;
 };
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
     const uint32_t s0 = sbase + (uint32_t)(it % p.stages) * p.stage_bytes;
     uint8_t* sp = smem + (size_t)(it % p.stages) * p.stage_bytes;
     if ((affine || relu) && !pool) {  // fused prologue, in place, on the chunks this thread copied
-      if (affine && o.n != ss_n) {
+      if (affine && !p.per_px_affine && o.n != ss_n) {
         const int64_t si = (d.in_bcast ? 0 : (int64_t)o.n * d.cin) + ca0 + my_c * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = d.in_scale[si + j]; sh[j] = d.in_shift[si + j]; }
@@ -232,6 +233,15 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const Params p) {
         const int pp = e >> p.cpa_sh;
         int ih = 0, iw = 0; int64_t m = 0;
         if (!pix_a(o, pp, ih, iw, m)) continue;
+        if (p.per_px_affine) {  // images smaller than a tile (8x8, 4x4 layers): the constants change inside the tile
+          const int nn = (int)fdiv((unsigned)m, p.fd_hw);
+          if (nn != ss_n) {
+            const int64_t si = (d.in_bcast ? 0 : (int64_t)nn * d.cin) + ca0 + my_c * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sc[j] = d.in_scale[si + j]; sh[j] = d.in_shift[si + j]; }
+            ss_n = nn;
+          }
+        }
         uint4* q = reinterpret_cast<uint4*>(sp + my_c * p.plane_a + pp * 16);
         float f[8];
         unpack8(*q, f);
@@ -584,7 +594,7 @@ static int wgrad_mma_plan(const iea_conv_desc* d, int g_dtype, int g_ld, wg::Par
   const int cin_eff = thin_a ? 16 : d->cin, cout_eff = thin_g ? 16 : d->cout;
   const bool is3 = d->ksize == 3;
   if (is3 && d->in_mode == IEA_IN_UP2 && (d->h % 2 || d->w % 2)) return 0;
-  if (!is3 && (((int64_t)d->h * d->w) % 128) && d->in_scale) return 0;  // a tile must not straddle images
+  p->per_px_affine = (!is3 && (((int64_t)d->h * d->w) % 128) && d->in_scale) ? 1 : 0;  // a tile straddles images
   if (!is3 && d->in_mode == IEA_IN_UP2) return 0;
   const int64_t M = d->n * (int64_t)d->h * d->w;
   if (M >= (1ll << 31) || M < 512) return 0;  // tiny problems stay on the generic kernel
