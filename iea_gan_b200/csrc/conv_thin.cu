@@ -739,6 +739,7 @@ static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint
   while (stages > 4 && p.stage_off + stages * G::STAGE + tail > 200 * 1024) stages -= 2;
   p.stages = stages;
   p.depth = stages >= 8 ? 3 : 2;  // items each group keeps in flight (it owns stages/2 slots)
+  { const char* e_ = getenv("IEA_THIN_DEPTH"); if (e_ && atoi(e_) >= 2 && atoi(e_) <= stages / 2) p.depth = atoi(e_); }  // tuning aid
   p.misc_off = p.stage_off + stages * G::STAGE;
   p.bar_off = (p.misc_off + misc + 15) / 16 * 16;
   smem = p.bar_off + 512;  // barriers: full, empty, landing (8 B x stages each), 2 x 4 accumulator, weights; TMEM slot
