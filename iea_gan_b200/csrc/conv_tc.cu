@@ -20,7 +20,9 @@ using namespace iea;
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int THREADS = 288;
+constexpr int THREADS = 416;   // warp 0: MMA issuer, warps 1-8: A producers, warps 9-12: epilogue
+constexpr int NPT = 256;       // producer threads (8 warps: a lone producer warp per scheduler walked ~550 dependent
+                               // instructions per K step; twice the warps, half the chunks per thread)
 
 struct Params {
   iea_conv_desc d;
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
   if (tid == 0) {
     // one arrival per producer WARP (+1: the expect_tx of the weight copy) -- 128 per-thread arrivals on one
     // mbarrier serialise and wake the parked MMA thread 128 times per step
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), NPT / 32 + 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -92,19 +94,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
         tc_commit(tfull_bar(ab));
       }
     }
-  } else if (warp <= 4) {
+  } else if (warp <= NPT / 32) {
     // ===================== A producers (+ weight TMA) =====================
+    constexpr int NCH = CPR * 128 / NPT;  // 16-byte chunks per thread and K step
     const int pt = tid - 32;
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tn = tile / p.n_tiles_m, tm = tile - tn * p.n_tiles_m;
       const int64_t m0 = (int64_t)tm * BM;
       const int n0 = tn * p.BN;
-      int r_[CPR], oh_[CPR], ow_[CPR];
-      int64_t n_[CPR];
+      int r_[NCH], oh_[NCH], ow_[NCH];
+      int64_t n_[NCH], base_[NCH];  // base_: element offset of (n, oh, ow) in a same-resolution input
 #pragma unroll
-      for (int i = 0; i < CPR; ++i) {
-        const int e = i * 128 + pt;
+      for (int i = 0; i < NCH; ++i) {
+        const int e = i * NPT + pt;
         r_[i] = e / CPR;
         const int64_t m = m0 + r_[i];
         if (m < p.M) {
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
         } else {
           ow_[i] = -100000; oh_[i] = -100000; n_[i] = 0;  // out of range -> zero rows
         }
+        base_[i] = ((n_[i] * p.hs + oh_[i]) * (int64_t)p.ws + ow_[i]) * d.x_ld;
       }
       const int cc = pt % CPR;  // chunk handled by this thread (e % CPR is the same for every i)
       // ---- software-pipelined path (same-resolution / nearest-up2 inputs): the raw 16-byte chunks of step
@@ -135,10 +139,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
         bf16* const tsc = reinterpret_cast<bf16*>(smem + p.tab_off);
         bf16* const tsh = tsc + TAB_IMGS * d.cin;
         if (affine) {
-          asm volatile("bar.sync 2, 128;" ::: "memory");  // every producer is done with the previous tile's table
+          asm volatile("bar.sync 2, 256;" ::: "memory");  // every producer is done with the previous tile's table
           if (tab) {
             const int c8n = d.cin >> 3;
-            for (int e = pt; e < nimg * c8n; e += 128) {
+            for (int e = pt; e < nimg * c8n; e += NPT) {
               const int li = e / c8n, c8 = e - li * c8n;
               const int64_t si = (d.in_bcast ? 0 : (img0 + li) * d.cin) + c8 * 8;
               float a[8], b[8];
@@ -150,21 +154,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
               *reinterpret_cast<uint4*>(tsh + li * d.cin + c8 * 8) = pack8(b);
             }
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 2, 256;" ::: "memory");
         }
-        uint4 nxt[CPR];
+        uint4 nxt[NCH];
         uint32_t nxt_ok = 0;
         auto raw_load = [&](int it) {
           const int tap = it / p.nkb, kb = it - tap * p.nkb;
           int dh = 0, dw = 0;
           if (d.ksize == 3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
           const int ci = kb * p.KB + cc * 8;
+          const int toff = (dh * p.ws + dw) * d.x_ld + ci;  // same-resolution input: one add per chunk
           nxt_ok = 0;
 #pragma unroll
-          for (int i = 0; i < CPR; ++i) {
+          for (int i = 0; i < NCH; ++i) {
             const int ih = oh_[i] + dh, iw = ow_[i] + dw;
             if ((unsigned)ih < (unsigned)d.h && (unsigned)iw < (unsigned)d.w) {
-              nxt[i] = __ldg(reinterpret_cast<const uint4*>(xb + ((n_[i] * p.hs + (ih >> sh_)) * (int64_t)p.ws + (iw >> sh_)) * d.x_ld + ci));
+              const bf16* src = sh_ ? xb + ((n_[i] * p.hs + (ih >> 1)) * (int64_t)p.ws + (iw >> 1)) * d.x_ld + ci
+                                    : xb + base_[i] + toff;
+              nxt[i] = __ldg(reinterpret_cast<const uint4*>(src));
               nxt_ok |= 1u << i;
             }
           }
@@ -173,10 +180,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
         for (int it = 0; it < k_iters; ++it, ++g) {
           const uint32_t s = g % p.stages, ph = (g / p.stages) & 1;
           const int tap = it / p.nkb, kb = it - tap * p.nkb;
-          uint4 cur[CPR];
+          uint4 cur[NCH];
           const uint32_t cur_ok = nxt_ok;
 #pragma unroll
-          for (int i = 0; i < CPR; ++i) cur[i] = nxt[i];
+          for (int i = 0; i < NCH; ++i) cur[i] = nxt[i];
           if (it + 1 < k_iters) raw_load(it + 1);
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t a0 = sbase + s * p.stage_bytes;
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
           }
           const int ci = kb * p.KB + cc * 8;
 #pragma unroll
-          for (int i = 0; i < CPR; ++i) {
+          for (int i = 0; i < NCH; ++i) {
             uint4 v = make_uint4(0, 0, 0, 0);
             if (cur_ok >> i & 1) {
               v = cur[i];
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const Params p) {
         if (d.ksize == 3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
         const int ci = kb * p.KB + cc * 8;
 #pragma unroll
-        for (int i = 0; i < CPR; ++i) {
+        for (int i = 0; i < NCH; ++i) {
           const uint4 v = load_chunk(d, p.hs, p.ws, n_[i], oh_[i] + dh, ow_[i] + dw, ci);
           *reinterpret_cast<uint4*>(smem + s * p.stage_bytes + cc * p.lbo_a + (r_[i] >> 3) * 128 + (r_[i] & 7) * 16) = v;
         }
