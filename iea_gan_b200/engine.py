@@ -28,13 +28,23 @@ from ._lib import call, ptr, dt
 IMGS = 40  # images per event (model.py:466)
 
 
+_ENV = os.environ._data if hasattr(os.environ, "_data") else None  # raw bytes mapping: no encode/decode per lookup
+
+
+def _env(name_b, name, default):
+    if _ENV is not None:
+        v = _ENV.get(name_b)
+        return default if v is None else v.decode()
+    return os.environ.get(name, default)
+
+
 def act_dtype():
-    return torch.float32 if os.environ.get("IEA_ACT_DTYPE", "bf16") == "fp32" else torch.bfloat16
+    return torch.float32 if _env(b"IEA_ACT_DTYPE", "IEA_ACT_DTYPE", "bf16") == "fp32" else torch.bfloat16
 
 
 def conv_impl():
     return {"auto": L.IMPL_AUTO, "generic": L.IMPL_GENERIC, "tcgen05": L.IMPL_TCGEN05}[
-        os.environ.get("IEA_CONV_IMPL", "auto")]
+        _env(b"IEA_CONV_IMPL", "IEA_CONV_IMPL", "auto")]
 
 
 LAUNCHES = [0]  # kernels launched through the C ABI (bench.py reports it)

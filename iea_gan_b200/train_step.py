@@ -13,7 +13,9 @@ from . import losses
 
 
 def toggle_grad(model, on):
-    for p in model.parameters():
+    """utils.toggle_grad (utils/__init__.py); also takes a cached parameter list (the module-tree walk of
+    .parameters() costs more host time than the whole optimizer step at this launch rate)."""
+    for p in (model if isinstance(model, (list, tuple)) else model.parameters()):
         p.requires_grad = on
 
 
@@ -35,7 +37,7 @@ def ortho_(model, strength=1e-4, blacklist=()):
     grad += strength * 2 (W W^T * (1 - I)) W, evaluated as 2 (W (W^T W) - diag(|w_i|^2) W) so the
     rows x rows Gram matrix (24576^2 for G.linear at H_base 3) is never formed."""
     with torch.no_grad():
-        for p in model.parameters():
+        for p in (model if isinstance(model, (list, tuple)) else model.parameters()):
             if p.dim() < 2 or any(p is b for b in blacklist) or p.grad is None:
                 continue
             w = p.view(p.shape[0], -1)
@@ -72,12 +74,14 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
     grad_hook(net) is called after each backward (the data-parallel all-reduce point)."""
     contra = losses.Conditional_Contrastive_loss(None, config["batch_size"], config["pos_collected_numerator"])
     state = state if state is not None else {"itr": 0}
+    g_params, d_params = list(G.parameters()), list(D.parameters())  # walked once, not ten times per step
+    g_black = list(G.shared.parameters())
 
     def train(x, y):
         G.optim.zero_grad()
         D.optim.zero_grad()
-        toggle_grad(D, True)
-        toggle_grad(G, False)
+        toggle_grad(d_params, True)
+        toggle_grad(g_params, False)
         t = 1.0
         # ---- D step (train_fns.py:49-139)
         z = z_.sample_()
@@ -91,13 +95,13 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
         if grad_hook is not None:
             grad_hook(D)
         if config.get("D_ortho", 0.0) > 0.0:
-            ortho_(D, config["D_ortho"])
+            ortho_(d_params, config["D_ortho"])
         if config.get("clip_norm") is not None:
-            torch.nn.utils.clip_grad_norm_(D.parameters(), config["clip_norm"])
+            torch.nn.utils.clip_grad_norm_(d_params, config["clip_norm"])
         D.optim.step()
         # ---- G step (train_fns.py:142-192)
-        toggle_grad(D, False)
-        toggle_grad(G, True)
+        toggle_grad(d_params, False)
+        toggle_grad(g_params, True)
         G.optim.zero_grad()
         z = z_.sample_()
         pf, ef, d_fake = GD(z, y, contra=True, train_G=True, split_D=True, diff_aug=config["diff_aug"])
@@ -108,9 +112,9 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
         if grad_hook is not None:
             grad_hook(G)
         if config.get("G_ortho", 0.0) > 0.0:
-            ortho_(G, config["G_ortho"], blacklist=list(G.shared.parameters()))
+            ortho_(g_params, config["G_ortho"], blacklist=g_black)
         if config.get("clip_norm") is not None:  # the reference only steps G inside this branch (train_fns.py:190-192)
-            torch.nn.utils.clip_grad_norm_(G.parameters(), config["clip_norm"])
+            torch.nn.utils.clip_grad_norm_(g_params, config["clip_norm"])
             G.optim.step()
         if ema is not None:
             ema.update(state["itr"])
