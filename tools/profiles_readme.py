@@ -51,7 +51,7 @@ if b:
         L += ["| 2 GPUs (weak scaling, 16 events/GPU sampling; 8 events/GPU training, NCCL gradient all-reduce) | %.1f events/s sampling, %.2f events/s training |" % (n2["value"], n2["train_step"]["value"])]
     L += ["", "Train-step timing noise: consecutive steps measured one by one (`tools/step_times.py`) take 174 ms (46 events/s) with",
           "sporadic 220-380 ms outliers at random steps (also with the Python GC disabled and with expandable allocator",
-          "segments): the step issues ~1900 launches from Python and sits near the host launch rate (98 ms per step at 1 event,",
+          "segments): the step issues ~1900 launches from Python and sits near the host launch rate (81 ms per step at 1 event,",
           "`tools/cpu_bound.py`), so any host-side hiccup on the shared box starves the GPU.  The bench lines are means over",
           "their K steps and therefore scatter between 31 and 46 events/s from run to run; the e2e leg and the median agree on ~45."]
     L += ["", "Clocks during the timed region: %s MHz of %s MHz, throttle reasons %s." % (b["clocks"]["sm_mhz"], b["clocks"]["sm_max_mhz"], b["clocks"]["reasons"] or "none")]
