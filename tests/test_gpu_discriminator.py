@@ -179,3 +179,55 @@ def test_train_step_vs_unmodified_train_fns(small_cfg, golden_step, adt):
             assert rel(D.state_dict()[k], v) < (1e-4 if adt == "fp32" else 3e-2), k
     finally:
         os.environ.pop("IEA_ACT_DTYPE", None)
+
+
+@pytest.mark.parametrize("adt,t_out,t_w,t_dx", [("bf16", 1e-2, 1.2e-1, 2.5e-1), ("fp32", 1e-5, 1e-3, 1e-2)])
+def test_full_size_discriminator_forward_backward_vs_oracle(adt, t_out, t_w, t_dx):
+    """BASELINE.json's shape (40 images of 256x256, shipped widths): the CUDA Discriminator -- stem on the
+    CUDA-core kernel, TMA-fed macro-tile tcgen05 convs, resident / streaming tcgen05 convs, tcgen05 attention
+    (1024 x 256, gamma != 0), cluster split-K head linears, macro-tile weight gradients -- against the fp32 CPU
+    oracle: the three outputs, the input gradient and weight gradients from the top, the middle (attention) and
+    the bottom of the net.
+    Tolerances.  fp32 activations (CUDA-core kernels, same arithmetic as the oracle in a different summation
+    order): outputs 1e-5, weight gradients 1e-3, input gradient 1e-2 -- the input gradient is per pixel and
+    passes 75 ReLU masks, a handful of which flip even at fp32 rounding level (measured 2.6e-3).  bf16
+    activations and gradients (the tensor-core path): outputs 1e-2 (measured 3.5e-3), weight gradients 1.2e-1
+    (measured 2-8 %, largest for the attention theta conv), input gradient 2.5e-1 (measured 0.18: no averaging
+    over pixels, and ~0.2 % of the ReLU masks of every layer differ from the fp32 forward)."""
+    import iea_gan_b200 as P
+    from iea_gan_b200.default_config import shipped_config
+    from oracle import iea_oracle as O
+    cfg = shipped_config(H_base=1, device="cuda")
+    torch.manual_seed(0)
+    D = P.Discriminator(**cfg)
+    with torch.no_grad():
+        D.blocks[2][2].gamma.fill_(0.5)  # the attention block must contribute
+    sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    torch.manual_seed(21)
+    x = torch.rand(40, 1, 256, 256) * 2 - 1
+    y = torch.arange(40)
+    go, ge = torch.randn(40), torch.randn(40, cfg["hypersphere_dim"])
+    names = ["input_conv.weight", "linear0.weight", "linear1.weight", "blocks.0.0.conv2.weight",
+             "blocks.2.2.theta.weight", "blocks.3.1.conv3.weight", "blocks.5.0.conv1.weight"]
+    os.environ["IEA_ACT_DTYPE"] = adt
+    try:
+        D = D.cuda().train()
+        xg = x.cuda().requires_grad_(True)
+        p, e, o = D(xg, y.cuda())
+        ((o * go.cuda()).sum() + (e * ge.cuda()).sum()).backward()
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)
+    got = {n: dict(D.named_parameters())[n].grad.detach().cpu() for n in names}
+    # oracle (fp32, CPU, autograd through the restated forward)
+    for n in names:
+        sd[n].requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    pr, er, orr = O.discriminator_forward(sd, dict(cfg, device="cpu"), xr, y, training=True)
+    ((orr * go).sum() + (er * ge).sum()).backward()
+    assert rel(p.detach(), pr) < 1e-5
+    assert rel(e.detach(), er) < t_out
+    assert rel(o.detach(), orr) < t_out
+    assert rel(xg.grad, xr.grad) < t_dx
+    for n in names:
+        assert rel(got[n], sd[n].grad) < t_w, n
