@@ -27,6 +27,7 @@ L = ["# profiles/ -- measured evidence, round %s" % R[1:], "",
      "| `launches_%s_{train8,sample16}.txt` | ncu `gpu__time_duration.sum` launch lists, summed per kernel | `tools/launch_summary.py` |" % R,
      "| `ncu_top_kernel_%s.txt` | `ncu --set full` of the macro-tile tcgen05 conv launches of one Generator forward (dominant kernel) | `tools/make_profiles.py` |" % R,
      "| `ncu_top_kernel_%s_stalls.txt` | warp-state samples per SASS line of the roofline launch | `tools/ncu_stalls.py` |" % R,
+     "| `ncu_attention_%s.txt` | `ncu --set full` of the tcgen05 / TMEM self-attention kernels (forward, query- and key-parallel backward) in a train step | `ncu -k regex:attn_` on `tools/prof_train.py` |" % R,
      "| `top_kernel_traffic.json` | DRAM bytes of the roofline launch (read by `bench.py` for `roofline.traffic`) | `tools/make_profiles.py` |", ""]
 if b:
     L += ["## Headline numbers (1 B200, bf16 activations, fp32 master weights, H_base = 1, synthetic data)", "",
