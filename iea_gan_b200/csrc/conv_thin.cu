@@ -760,9 +760,8 @@ static int thin_launch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
   thin::Params p; int grid = 0; uint32_t smem = 0;
   alignas(64) CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
-  // TMA producer: same-resolution bf16 input and a producer-paced shape (16 output channels: with 32 the epilogue
-  // paces the kernel); IEA_THIN_TMA=0 keeps the cp.async producer (tests cover both)
-  constexpr bool TMA_OK = NB == 1 || IS3 || CPR >= 4;  // (16 -> 32 1x1: the epilogue paces the kernel, nothing to gain)
+  // TMA producer: same-resolution bf16 input; IEA_THIN_TMA=0 keeps the cp.async producer (tests cover both)
+  constexpr bool TMA_OK = true;  // (also worth it where the epilogue paces the kernel: 16 -> 32 1x1 + residual 2.05 -> 1.79 ms)
   bool tma = TMA_OK && !grid_only && d->in_mode == IEA_IN_DIRECT && d->x_ld % 8 == 0;
   if (tma) { const char* e_ = getenv("IEA_THIN_TMA"); if (e_ && e_[0] == '0') tma = false; }
   if (tma) tma = thin_tensor_map(d, IS3, MT, &tm);
