@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_window(const void* b, int dtype, int ld, co
 
 // ---------------------------------------------------------------- forward / data gradient: 1 -> C
 template <int CG>
-__global__ void __launch_bounds__(256) c1_fwd_kernel(const iea_conv_desc d, const Geo g) {
+__global__ void __launch_bounds__(256, 2) c1_fwd_kernel(const iea_conv_desc d, const Geo g) {
   const int cg = threadIdx.x % CG;
   float2 w2[9][4], b2[4];
   {
