@@ -70,7 +70,7 @@ _SIG = {
     "iea_colsum": [vp, i32, i32, i64, i32, vp, f32, vp, vp],
     "iea_residual_bwd": [vp, i32, i32, i64, i32, i32, i32, i32, vp, i32, i32, i32, f32, vp],
     "iea_bn_stats": [vp, i32, i32, i64, i32, i32, i32, vp, vp],
-    "iea_bn_finalize": [vp, i32, i32, i64, i32, i32, vp, i64, f32, vp, i64, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp],
+    "iea_bn_finalize": [vp, i32, i32, i64, i32, i32, vp, i64, f32, vp, i64, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp, vp],
     "iea_bn_finalize_bwd": [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp, i64, f32, vp, i64, vp, i64, i32, i32, vp, vp, vp],
     "iea_affine_act": [vp, i32, vp, vp, i64, i64, i32, i32, vp, i32, vp],
     "iea_nchw_to_nhwc": [vp, i32, vp, i32, i64, i32, i64, vp],
@@ -98,6 +98,8 @@ _SIG = {
     "iea_loss_hinge_dis_bwd": [vp, vp, vp, i64, vp, vp, vp],
     "iea_loss_mean": [vp, i64, f32, vp, vp],
     "iea_loss_mean_bwd": [vp, i64, f32, vp, vp],
+    "iea_loss_l2": [vp, vp, i64, vp, vp],
+    "iea_loss_l2_bwd": [vp, vp, vp, i64, vp, vp, vp],
     "iea_loss_contrastive_fwd": [vp, vp, i32, i32, i32, f32, f32, vp, vp, vp],
     "iea_loss_contrastive_bwd": [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp],
     "iea_loss_iea_fwd": [vp, vp, i32, i32, i32, vp, vp, vp],

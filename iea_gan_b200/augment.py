@@ -11,23 +11,24 @@ identity for the single-channel PXD images and only consumes its draw.
 import torch
 
 from . import engine as E
+from . import noise
 
 
 def _draw_color(x, which):
-    return torch.rand(x.size(0), 1, 1, 1, dtype=torch.float32, device=x.device)
+    return noise.rand((x.size(0), 1, 1, 1), x.device)
 
 
 def _draw_translation(x, ratio=0.125):
     sx, sy = int(x.size(2) * ratio + 0.5), int(x.size(3) * ratio + 0.5)
-    tx = torch.randint(-sx, sx + 1, size=[x.size(0), 1, 1], device=x.device)
-    ty = torch.randint(-sy, sy + 1, size=[x.size(0), 1, 1], device=x.device)
+    tx = noise.randint(-sx, sx + 1, [x.size(0), 1, 1], x.device)
+    ty = noise.randint(-sy, sy + 1, [x.size(0), 1, 1], x.device)
     return tx, ty
 
 
 def _draw_cutout(x, ratio=0.5):
     ch, cw = int(x.size(2) * ratio + 0.5), int(x.size(3) * ratio + 0.5)
-    ox = torch.randint(0, x.size(2) + (1 - ch % 2), size=[x.size(0), 1, 1], device=x.device)
-    oy = torch.randint(0, x.size(3) + (1 - cw % 2), size=[x.size(0), 1, 1], device=x.device)
+    ox = noise.randint(0, x.size(2) + (1 - ch % 2), [x.size(0), 1, 1], x.device)
+    oy = noise.randint(0, x.size(3) + (1 - cw % 2), [x.size(0), 1, 1], x.device)
     return ox, oy, ch, cw
 
 

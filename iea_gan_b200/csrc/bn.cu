@@ -8,6 +8,18 @@ using namespace iea;
 
 namespace {
 
+// running statistics <- one event's batch statistics.  mode bits (iea_bn_finalize): 1 training
+// (F.batch_norm: momentum update with the UNBIASED variance, layers.py:664-673); 2 myBN (momentum
+// update with the biased variance, layers.py:585-592); 4 myBN standing statistics (plain sums,
+// layers.py:579-582).
+__device__ __forceinline__ void fold_running(float& rm, float& rv, float mean, double var, double count,
+                                             float momentum, int mode) {
+  if (mode & 4) { rm += mean; rv += (float)var; return; }
+  const double v = (mode & 2) ? var : (count > 1.0 ? var * count / (count - 1.0) : var);
+  rm = (1.f - momentum) * rm + momentum * mean;
+  rv = (1.f - momentum) * rv + momentum * (float)v;
+}
+
 // partials[e][t][c][2]; grid (events*tiles, channel chunks)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const void* x, int x_dtype, int x_ld, int rows_per_event, int c,
                                                        int tiles, float* partials, int cb) {
@@ -102,9 +114,7 @@ __global__ void bn_running_kernel(int events, double count, int c, float* stored
   float rm = stored_mean ? stored_mean[cc] : 0.f, rv = stored_var ? stored_var[cc] : 1.f;
   for (int e = 0; e < events; ++e) {
     const double var = (double)rstd_io[e * c + cc];
-    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-    rm = (1.f - momentum) * rm + momentum * mean_io[e * c + cc];
-    rv = (1.f - momentum) * rv + momentum * (float)unb;
+    fold_running(rm, rv, mean_io[e * c + cc], var, count, momentum, training);
     rstd_io[e * c + cc] = (float)(1.0 / sqrt(var + (double)eps));  // variance -> rstd, saved for backward
   }
   if (stored_mean) { stored_mean[cc] = rm; stored_var[cc] = rv; }
@@ -178,8 +188,10 @@ __global__ void affine_act_kernel(const void* x, int x_dtype, const float* scale
 // (ticket counter) then does everything that needs all events of those channels: running-statistics update in
 // event order, variance -> rstd, and the per-image scale / shift the consumer convolution's prologue reads.
 // Fixed summation orders throughout: deterministic, whichever block ends up last.
-__device__ unsigned int g_bn_ticket[1024];  // self-resetting; one entry per 8-channel group
-__global__ void __launch_bounds__(256) bn_finalize_fused_kernel(const float* partials, int tiles, double count, int events,
+// `ticket` is caller-owned (one self-resetting counter per 8-channel group, zero before the first use): every
+// batch-norm layer passes its own, so finalize launches in flight on different streams never share counters.
+__global__ void __launch_bounds__(256) bn_finalize_fused_kernel(unsigned int* g_bn_ticket, int mode,
+                                                                const float* partials, int tiles, double count, int events,
                                                                 int imgs, int c, const float* gain, int64_t gain_ld,
                                                                 float gain_add, const float* bias, int64_t bias_ld,
                                                                 float* stored_mean, float* stored_var, float momentum,
@@ -257,12 +269,8 @@ __global__ void __launch_bounds__(256) bn_finalize_fused_kernel(const float* par
   __syncthreads();
   if (tl == 0 && cc < c) {
     float rm = stored_mean ? stored_mean[cc] : 0.f, rv = stored_var ? stored_var[cc] : 1.f;
-    for (int ev = 0; ev < events; ++ev) {
-      const double var = (double)v_s[ev * 8 + cl];
-      const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-      rm = (1.f - momentum) * rm + momentum * m_s[ev * 8 + cl];
-      rv = (1.f - momentum) * rv + momentum * (float)unb;
-    }
+    for (int ev = 0; ev < events; ++ev)
+      fold_running(rm, rv, m_s[ev * 8 + cl], (double)v_s[ev * 8 + cl], count, momentum, mode);
     if (stored_mean) { stored_mean[cc] = rm; stored_var[cc] = rv; }
   }
   for (int i = threadIdx.x; i < events * 8; i += 256) {
@@ -288,17 +296,19 @@ extern "C" int iea_bn_stats(const void* x, int x_dtype, int x_ld, int64_t rows, 
 extern "C" int iea_bn_finalize(const float* partials, int events, int tiles_per_event, int64_t count_per_event,
                                int imgs_per_event, int c, const float* gain, int64_t gain_ld, float gain_add,
                                const float* bias, int64_t bias_ld, float* stored_mean, float* stored_var,
-                               int training, float momentum, float eps, float* mean_out, float* rstd_out,
-                               float* scale, float* shift, iea_stream_t stream) {
+                               int mode, float momentum, float eps, float* mean_out, float* rstd_out,
+                               float* scale, float* shift, unsigned int* ticket, iea_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)events * imgs_per_event;
-  if (training && events <= 64 && c <= 8 * 1024) {
+  const int training = mode;  // (bit 0 set <=> batch statistics; the other bits choose the running-statistics rule)
+  IEA_CHECK_ARG(!(mode & 6) || (mode & 1), "iea_bn_finalize: myBN mode bits (%d) need the training bit", mode);
+  if ((mode & 1) && ticket && events <= 64) {
     bn_finalize_fused_kernel<<<dim3(events, cdiv(c, 8)), 256, 0, st>>>(
-        partials, tiles_per_event, (double)count_per_event, events, imgs_per_event, c, gain, gain_ld, gain_add, bias, bias_ld,
+        ticket, mode, partials, tiles_per_event, (double)count_per_event, events, imgs_per_event, c, gain, gain_ld, gain_add, bias, bias_ld,
         stored_mean, stored_var, momentum, eps, mean_out, rstd_out, scale, shift);
     return check_launch("iea_bn_finalize(fused)");
   }
-  if (training)
+  if (mode & 1)
     bn_reduce_kernel<<<dim3(events, cdiv(c, 8)), 256, 0, st>>>(partials, tiles_per_event, (double)count_per_event, c,
                                                                  mean_out, rstd_out);
   bn_affine_kernel<<<cdiv(n * c, 256), 256, 0, st>>>(events, (double)count_per_event, imgs_per_event, c, gain, gain_ld,

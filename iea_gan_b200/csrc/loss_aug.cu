@@ -117,6 +117,21 @@ __global__ void mean_bwd_kernel(const float* dout, int64_t n, float scale, float
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dx[i] = dout[0] * scale / n;
 }
+// loss.py:41-44 l2_loss = MSELoss(a, b): single block, fixed-order reduction (the inputs are (40E,) logits)
+__global__ void __launch_bounds__(256) l2_kernel(const float* a, const float* b, int64_t n, float* out) {
+  __shared__ float red[33];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float d = a[i] - b[i]; s = fmaf(d, d, s); }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s / n;
+}
+__global__ void l2_bwd_kernel(const float* a, const float* b, const float* dout, int64_t n, float* da, float* db) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = 2.f * (a[i] - b[i]) * dout[0] / n;
+  if (da) da[i] = g;
+  if (db) db[i] = -g;
+}
 __global__ void sum_events_kernel(const float* ev, int events, int stride, float* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float t = 0.f;
@@ -365,6 +380,15 @@ int iea_loss_mean(const float* x, int64_t n, float scale, float* out, iea_stream
 int iea_loss_mean_bwd(const float* dout, int64_t n, float scale, float* dx, iea_stream_t st) {
   mean_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(dout, n, scale, dx);
   return check_launch("iea_loss_mean_bwd");
+}
+int iea_loss_l2(const float* a, const float* b, int64_t n, float* out, iea_stream_t st) {
+  l2_kernel<<<1, 256, 0, (cudaStream_t)st>>>(a, b, n, out);
+  return check_launch("iea_loss_l2");
+}
+int iea_loss_l2_bwd(const float* a, const float* b, const float* dout, int64_t n, float* da, float* db,
+                    iea_stream_t st) {
+  l2_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(a, b, dout, n, da, db);
+  return check_launch("iea_loss_l2_bwd");
 }
 int iea_loss_contrastive_fwd(const float* embed, const float* proxy, int events, int seq, int dim, float temperature,
                              float margin, float* loss, float* saved, iea_stream_t st) {

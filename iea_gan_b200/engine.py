@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import noise
 from ._lib import call, ptr, dt
 
 IMGS = 40  # images per event (model.py:466)
@@ -77,6 +78,30 @@ def K(name, *args, launches=1):
 
 def cdiv(a, b):
     return (a + b - 1) // b
+
+
+def on_tensor_device(fn):
+    """Run an entry point with the CUDA device of its first tensor / module argument current: the C ABI launches
+    on the current device's stream, so a net living on cuda:1 while cuda:0 is current must switch first."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                dev = a.device
+            elif isinstance(a, torch.nn.Module):
+                dev = next((t.device for t in a.parameters()), None)
+            elif isinstance(a, (list, tuple)) and a and isinstance(a[0], torch.nn.Module):
+                dev = next((t.device for t in a[0].parameters()), None)
+            if dev is not None:
+                break
+        if dev is None or dev.type != "cuda" or dev.index is None or dev.index == torch._C._cuda_getDevice():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapped
 
 
 # ------------------------------------------------------------------ tape
@@ -386,10 +411,10 @@ def _desc(n, h, w, cin, cout, k, x_t, x_ptr, x_ld, in_mode, in_relu, scale, shif
 
 class ScaleShift:
     """Per-(image, channel) affine of a batch-norm, consumed by a conv prologue."""
-    __slots__ = ("scale", "shift", "dscale", "dshift")
+    __slots__ = ("scale", "shift", "dscale", "dshift", "mean", "rstd")
 
-    def __init__(self, scale, shift):
-        self.scale, self.shift, self.dscale, self.dshift = scale, shift, None, None
+    def __init__(self, scale, shift, mean=None, rstd=None):
+        self.scale, self.shift, self.dscale, self.dshift, self.mean, self.rstd = scale, shift, None, None, mean, rstd
 
 
 def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu=False, ss=None, res=None,
@@ -527,8 +552,19 @@ def ensure_stats(xv, n, h, w):
     return xv.bn
 
 
+def _ticket(owner, c, dev):
+    """Per-layer self-resetting counters of the one-launch finalize (caller-owned: include/iea_b200.h)."""
+    t = owner.__dict__.get("_iea_ticket") if owner is not None else None
+    if t is None or t.device != dev or t.numel() < cdiv(c, 8):
+        t = torch.zeros(cdiv(c, 8), dtype=torch.int32, device=dev)
+        if owner is not None:
+            owner.__dict__["_iea_ticket"] = t
+    return t
+
+
 def bn_affine(tape, xv, n, h, w, *, gain, gain_ld, gain_add, bias, bias_ld, stored_mean, stored_var, training,
-              eps, momentum=0.1, dgain=None, dbias=None, dgb_ld=0, gain_param=None, bias_param=None):
+              eps, momentum=0.1, dgain=None, dbias=None, dgb_ld=0, gain_param=None, bias_param=None, owner=None,
+              mode=None):
     """Finalize the batch statistics of xv into a per-(n,c) ScaleShift (layers.py:656-689, 728-742).
     ccbn: gain/bias are raw device addresses of column windows of the grouped-GEMM output (row
     stride gain_ld) and dgain/dbias the matching windows of its gradient buffer; plain bn:
@@ -540,9 +576,9 @@ def bn_affine(tape, xv, n, h, w, *, gain, gain_ld, gain_add, bias, bias_ld, stor
     mean = torch.empty((events, c), dtype=torch.float32, device=dev)
     rstd = torch.empty((events, c), dtype=torch.float32, device=dev)
     K("iea_bn_finalize", ptr(part), events, tiles, count, IMGS, c, gain, gain_ld, gain_add, bias, bias_ld,
-      ptr(stored_mean), ptr(stored_var), int(training), momentum, eps, ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
-      L.stream())
-    ss = ScaleShift(scale, shift)
+      ptr(stored_mean), ptr(stored_var), int(training) if mode is None else mode, momentum, eps, ptr(mean), ptr(rstd),
+      ptr(scale), ptr(shift), ptr(_ticket(owner, c, dev)) if training else None, L.stream())
+    ss = ScaleShift(scale, shift, mean, rstd)
     if tape.record:
         def bw():
             if ss.dscale is None:
@@ -748,6 +784,22 @@ def _plan(net, cls):
     return p[1]
 
 
+def bn_state(bnm):
+    """(stored_mean, stored_var, mode, owner) of a ccbn / bn module: F.batch_norm running statistics
+    (layers.py:664-673, 733-742) or, with mybn=True, the myBN child's (layers.py:547-599: biased variance,
+    optional standing-statistics accumulation; eval divides standing sums by the counter)."""
+    if not getattr(bnm, "mybn", False):
+        return bnm.stored_mean, bnm.stored_var, int(bnm.training), bnm
+    b = bnm.bn
+    if bnm.training:
+        if b.accumulate_standing:
+            b.accumulation_counter += 1.0
+        return b.stored_mean, b.stored_var, (1 | 4) if b.accumulate_standing else (1 | 2), b
+    if b.accumulate_standing:
+        return b.stored_mean / b.accumulation_counter, b.stored_var / b.accumulation_counter, 0, b
+    return b.stored_mean, b.stored_var, 0, b
+
+
 def _gblock(tape, blk, x, n, hh, ww, plan, gb, dgb, training):
     """One bottleneck GBlock as 4 fused convs (model.py:54-71): every ccbn+ReLU(+upsample) is the
     prologue of the conv that consumes it, every conv's epilogue emits the next BN's statistics, and
@@ -758,9 +810,11 @@ def _gblock(tape, blk, x, n, hh, ww, plan, gb, dgb, training):
 
     def aff(bnm, xv, h, w):
         g0, b0 = plan.gb_off[bnm]
+        sm, sv, mode, owner = bn_state(bnm)
         return bn_affine(tape, xv, n, h, w, gain=gb.data_ptr() + 4 * g0, gain_ld=gld, gain_add=1.0,
-                         bias=gb.data_ptr() + 4 * b0, bias_ld=gld, stored_mean=bnm.stored_mean,
-                         stored_var=bnm.stored_var, training=training, eps=bnm.eps,
+                         bias=gb.data_ptr() + 4 * b0, bias_ld=gld, stored_mean=sm,
+                         stored_var=sv, training=training, eps=bnm.eps, owner=owner, mode=mode,
+                         momentum=bnm.momentum if getattr(bnm, "mybn", False) else 0.1,  # layers.py:671 hard-codes 0.1
                          dgain=(dgb.data_ptr() + 4 * g0) if dgb is not None else None,
                          dbias=(dgb.data_ptr() + 4 * b0) if dgb is not None else None, dgb_ld=gld)
     h1 = conv(tape, x, h_[blk.conv1], n, hh, ww, 1, bias=blk.conv1.bias, in_relu=True,
@@ -805,9 +859,10 @@ def _g_body(G, tape, z, y, rdof):
         for blk in bl:
             h, hh, ww = _gblock(tape, blk, h, n, hh, ww, plan, gb, dgb, training)
     obn, oconv = G.output_layer[0], G.output_layer[2]
+    sm, sv, mode, owner = bn_state(obn)
     ss = bn_affine(tape, h, n, hh, ww, gain=ptr(obn.gain), gain_ld=0, gain_add=0.0, bias=ptr(obn.bias), bias_ld=0,
-                   stored_mean=obn.stored_mean, stored_var=obn.stored_var, training=training, eps=obn.eps,
-                   momentum=obn.momentum, gain_param=obn.gain, bias_param=obn.bias)
+                   stored_mean=sm, stored_var=sv, training=training, eps=obn.eps,
+                   momentum=obn.momentum, gain_param=obn.gain, bias_param=obn.bias, owner=owner, mode=mode)
     img = conv(tape, h, h_[oconv], n, hh, ww, 3, bias=oconv.bias, in_relu=True, ss=ss, act=L.ACT_TANH,
                out_dtype=torch.float32)
     return img, hh, ww
@@ -858,12 +913,13 @@ def _plain(t, dtype=torch.float32):
     return t.contiguous() if t.dtype == dtype else t.to(dtype).contiguous()
 
 
+@on_tensor_device
 def generator_forward(G, z, y):
     z = _plain(z)
     L.require_device(z)
     n = z.shape[0]
     # same draw as model.py:466: torch.randn on the device generator before anything else (40E rows)
-    rdof = torch.randn(n, G.rdof_dim, device=z.device)
+    rdof = noise.randn(n, G.rdof_dim, z.device)
     y = _plain(y, torch.int64)
     geo = {}
 
@@ -875,6 +931,7 @@ def generator_forward(G, z, y):
     return out.view(n, 1, *geo["hw"])  # one channel: NHWC and NCHW coincide
 
 
+@on_tensor_device
 def adu_postprocess(img):
     n, _, h, w = img.shape
     img = img.contiguous()
@@ -1056,6 +1113,7 @@ def _d_body(D, tape, xv, y, hh, ww):
     return [proxy, e, out]
 
 
+@on_tensor_device
 def discriminator_forward(D, x, y):
     x = _plain(x)
     L.require_device(x)
@@ -1107,6 +1165,7 @@ class _AugFn(torch.autograd.Function):
         return dx, None
 
 
+@on_tensor_device
 def diffaug_apply(x, draws):
     """One fused pass over the image for whichever of brightness / contrast / translation / cutout
     `draws` holds (saturation is the identity for one channel; its draw is only consumed)."""
@@ -1140,6 +1199,7 @@ def _events(x):
     return n // IMGS
 
 
+@on_tensor_device
 def loss_hinge_dis(dis_fake, dis_real):
     f, r = _plain(dis_fake).view(-1), _plain(dis_real).view(-1)
     L.require_device(f)
@@ -1160,6 +1220,7 @@ def loss_hinge_dis(dis_fake, dis_real):
     return loss_real, loss_fake
 
 
+@on_tensor_device
 def _mean_loss(x, scale):
     x = _plain(x).view(-1)
     L.require_device(x)
@@ -1181,10 +1242,28 @@ def loss_hinge_gen(dis_fake):
     return _mean_loss(dis_fake, -1.0)
 
 
+@on_tensor_device
 def loss_l2(a, b):
-    raise NotImplementedError("l2_loss is only reached with Con_reg=True (config.json:99 Con_reg=false)")
+    """loss.l2_loss = MSELoss (loss.py:41-44; the consistency-regularisation term of train_fns.py:75-77)."""
+    a, b = _plain(a).reshape(-1), _plain(b).reshape(-1)
+    L.require_device(a)
+    n = a.numel()
+    if b.numel() != n:
+        raise ValueError("l2_loss: operands of %d and %d elements" % (n, b.numel()))
+
+    def fwd(a, b):
+        out = _f32(1, a.device)
+        K("iea_loss_l2", ptr(a), ptr(b), n, ptr(out), L.stream())
+        return out[0], None
+
+    def bwd(saved, xs, g, need):
+        da, db = torch.empty_like(xs[0]), torch.empty_like(xs[1])
+        K("iea_loss_l2_bwd", ptr(xs[0]), ptr(xs[1]), ptr(g[0]), n, ptr(da), ptr(db), L.stream())
+        return da, db
+    return _LossFn.apply(fwd, bwd, a, b)
 
 
+@on_tensor_device
 def loss_contrastive(embed, proxy, temperature, margin):
     e, p = _plain(embed), _plain(proxy)
     L.require_device(e)
@@ -1205,6 +1284,7 @@ def loss_contrastive(embed, proxy, temperature, margin):
     return _LossFn.apply(fwd, bwd, e, p)
 
 
+@on_tensor_device
 def loss_iea(k_f, k_r):
     f, r = _plain(k_f), _plain(k_r).detach()
     L.require_device(f)
@@ -1223,6 +1303,7 @@ def loss_iea(k_f, k_r):
     return _LossFn.apply(fwd, bwd, f, r)
 
 
+@on_tensor_device
 def loss_uniformity(x, t):
     x = _plain(x)
     L.require_device(x)
@@ -1263,8 +1344,15 @@ def _to_nhwc(tape, x4):
         def bw():
             if ov.g is None or not x4.need:
                 return
+            g = ov.g
+            if ov.ds is not None:  # gradient through the batch statistics of a batch-norm that consumed `out`
+                ds1, ds2, rpe = ov.ds
+                ge = torch.empty_like(g)
+                K("iea_conv_out_bwd", ptr(g), dt(g), c, ptr(out), dt(out), c, 0, ptr(ds1), ptr(ds2), n * hh * ww,
+                  rpe, c, ptr(ge), dt(ge), L.stream())
+                g = ge
             dx = torch.empty_like(x4.t)
-            K("iea_nhwc_to_nchw", ptr(ov.g), dt(ov.g), ptr(dx), dt(dx), n, c, hh * ww, L.stream())
+            K("iea_nhwc_to_nchw", ptr(g), dt(g), ptr(dx), dt(dx), n, c, hh * ww, L.stream())
             add_grad(x4, dx)
         tape.add(bw)
     return ov
@@ -1286,6 +1374,7 @@ def _to_nchw(tape, xv, n, hh, ww, dtype=torch.float32):
     return ov
 
 
+@on_tensor_device
 def module_conv(m, x):
     x = _plain(x)
     L.require_device(x)
@@ -1299,6 +1388,7 @@ def module_conv(m, x):
     return run_net(body, [x], list(m.parameters()))
 
 
+@on_tensor_device
 def module_linear(m, x):
     x = _plain(x)
     L.require_device(x)
@@ -1312,6 +1402,7 @@ def module_linear(m, x):
     return run_net(body, [x2], list(m.parameters())).view(*lead, -1)
 
 
+@on_tensor_device
 def module_embedding(m, idx):
     L.require_device(m.weight)
     grp, hs = _mod_plan(m, [m], [torch.float32])
@@ -1323,6 +1414,7 @@ def module_embedding(m, idx):
     return run_net(body, [], list(m.parameters())).view(*idx.shape, -1)
 
 
+@on_tensor_device
 def sn_weight_standalone(m):
     """SN.W_(): weight / sigma, differentiable w.r.t. weight (layers.py:151-165)."""
     L.require_device(m.weight)
@@ -1354,6 +1446,7 @@ def sn_weight_standalone(m):
     return run_net(body, [], [m.weight]).view_as(m.weight)
 
 
+@on_tensor_device
 def power_iteration_single(W, u, update, eps):
     """layers.power_iteration for one singular vector, on the grouped kernel."""
     L.require_device(W)
@@ -1370,6 +1463,7 @@ def power_iteration_single(W, u, update, eps):
     return m.sv0[0].clone(), m.u0.clone(), l.v().view(1, -1).clone()
 
 
+@on_tensor_device
 def module_bn(m, x):
     """layers.bn.forward as stats + affine kernels (stand-alone use; inside G it is fused)."""
     x = _plain(x)
@@ -1378,11 +1472,68 @@ def module_bn(m, x):
 
     def body(tape, xv):
         xn = _to_nhwc(tape, xv)
+        sm, sv, mode, owner = bn_state(m)
         ss = bn_affine(tape, xn, n, hh, ww, gain=ptr(m.gain), gain_ld=0, gain_add=0.0, bias=ptr(m.bias), bias_ld=0,
-                       stored_mean=m.stored_mean, stored_var=m.stored_var, training=m.training, eps=m.eps,
-                       momentum=m.momentum, gain_param=m.gain, bias_param=m.bias)
+                       stored_mean=sm, stored_var=sv, training=m.training, eps=m.eps,
+                       momentum=m.momentum, gain_param=m.gain, bias_param=m.bias, owner=owner, mode=mode)
         return [_to_nchw(tape, affine(tape, xn, ss, n, hh * ww, False), n, hh, ww)]
     return run_net(body, [x], list(m.parameters()))
+
+
+@on_tensor_device
+def bn_functional(x, gain, bias, *, stored_mean, stored_var, training, mode, eps, momentum, owner=None,
+                  want_stats=False):
+    """Batch-norm with caller-supplied per-sample (N,C) or per-channel (1,C) gain / bias TENSORS (autograd
+    flows into them): the arithmetic of myBN.forward / manual_bn / fused_bn (layers.py:505-599).
+    training: batch statistics per event (running statistics per `mode`, see iea_bn_finalize);
+    otherwise the given stored statistics."""
+    x = _plain(x)
+    L.require_device(x)
+    n, c, hh, ww = x.shape
+    dev = x.device
+
+    def rows(t, fill):
+        if t is None:
+            return torch.full((n, c), fill, dtype=torch.float32, device=dev)
+        return _plain(t).reshape(-1, c).expand(n, c).contiguous()
+    g2, b2 = rows(gain, 1.0), rows(bias, 0.0)
+    keep = {}
+
+    def body(tape, xv, gv, bv):
+        xn = _to_nhwc(tape, xv)
+        dgb = torch.zeros((n, 2 * c), dtype=torch.float32, device=dev) if tape.record else None
+        if tape.record:
+            def bw():  # (added first: runs after the finalize backward has filled dgb)
+                gv.g, bv.g = dgb[:, :c].contiguous(), dgb[:, c:].contiguous()
+            tape.add(bw)
+        ss = bn_affine(tape, xn, n, hh, ww, gain=gv.t.data_ptr(), gain_ld=c, gain_add=0.0, bias=bv.t.data_ptr(),
+                       bias_ld=c, stored_mean=stored_mean, stored_var=stored_var, training=training, eps=eps,
+                       momentum=momentum, dgain=dgb.data_ptr() if dgb is not None else None,
+                       dbias=(dgb.data_ptr() + 4 * c) if dgb is not None else None, dgb_ld=2 * c, owner=owner,
+                       mode=mode)
+        keep["ss"] = ss
+        return [_to_nchw(tape, affine(tape, xn, ss, n, hh * ww, False), n, hh, ww)]
+    out = run_net(body, [x, g2, b2], [])
+    if want_stats:
+        ss = keep["ss"]
+        return out, ss.mean, (ss.rstd.double().pow(-2) - eps).float()
+    return out
+
+
+def module_mybn(m, x, gain, bias):
+    """myBN.forward(x, gain, bias) (layers.py:570-599)."""
+    if m.training:
+        if m.accumulate_standing:
+            m.accumulation_counter += 1.0
+        mode = (1 | 4) if m.accumulate_standing else (1 | 2)
+        sm, sv = m.stored_mean, m.stored_var
+    else:
+        mode = 0
+        sm, sv = m.stored_mean, m.stored_var
+        if m.accumulate_standing:
+            sm, sv = sm / m.accumulation_counter, sv / m.accumulation_counter
+    return bn_functional(x, gain, bias, stored_mean=sm, stored_var=sv, training=m.training, mode=mode, eps=m.eps,
+                         momentum=m.momentum, owner=m)
 
 
 def affine(tape, xv, ss, n, hw, relu):
@@ -1407,6 +1558,7 @@ def affine(tape, xv, ss, n, hw, relu):
     return yv
 
 
+@on_tensor_device
 def module_ccbn(m, x, y):
     """layers.ccbn.forward stand-alone: the two SNLinears as one grouped GEMM, stats, affine."""
     x, y = _plain(x), _plain(y)
@@ -1431,20 +1583,61 @@ def module_ccbn(m, x, y):
             dgb = torch.zeros_like(gb)
             gbv.g = dgb
         xn = _to_nhwc(tape, xv)
+        sm, sv, mode, owner = bn_state(m)
         ss = bn_affine(tape, xn, n, hh, ww, gain=gb.data_ptr(), gain_ld=2 * c, gain_add=1.0,
-                       bias=gb.data_ptr() + 4 * c, bias_ld=2 * c, stored_mean=m.stored_mean,
-                       stored_var=m.stored_var, training=m.training, eps=m.eps,
+                       bias=gb.data_ptr() + 4 * c, bias_ld=2 * c, stored_mean=sm,
+                       stored_var=sv, training=m.training, eps=m.eps, momentum=m.momentum if m.mybn else 0.1, owner=owner,
+                       mode=mode,
                        dgain=dgb.data_ptr() if dgb is not None else None,
                        dbias=(dgb.data_ptr() + 4 * c) if dgb is not None else None, dgb_ld=2 * c)
         return [_to_nchw(tape, affine(tape, xn, ss, n, hh * ww, False), n, hh, ww)]
     return run_net(body, [x, y], list(m.parameters()))
 
 
+class _BlockPlan:
+    """SN group of one stand-alone GBlock: its four convs + the eight ccbn linears as one grouped GEMM."""
+
+    def __init__(self, blk):
+        self.sn = SNGroup()
+        self.h = {cv: self.sn.add(cv, act_dtype()) for cv in (blk.conv1, blk.conv2, blk.conv3, blk.conv4)}
+        mods, off, self.gb_off = [], 0, {}
+        for b in (blk.bn1, blk.bn2, blk.bn3, blk.bn4):
+            self.gb_off[b] = (off, off + b.output_size)
+            off += 2 * b.output_size
+            mods += [b.gain, b.bias]
+        self.gb_cols = off
+        self.gb_layers = self.sn.add_shared(mods, torch.float32)
+
+
+@on_tensor_device
 def module_gblock(blk, x, y):
-    raise NotImplementedError("GBlock is executed inside Generator.forward (its ccbn linears are part of the "
-                              "net-level grouped GEMM); call the Generator")
+    """GBlock.forward(x, y) stand-alone (model.py:54-71): the same four fused convs as inside the Generator,
+    with this block's eight ccbn gain / bias linears as one grouped GEMM on y."""
+    x, y = _plain(x), _plain(y)
+    L.require_device(x)
+    for b in (blk.bn1, blk.bn2, blk.bn3, blk.bn4):
+        if not hasattr(b, "gain") or not hasattr(b.gain, "weight"):
+            raise NotImplementedError("stand-alone GBlock is built for which_bn=ccbn (the Generator's)")
+    plan = _plan(blk, _BlockPlan)
+    n, _, hh, ww = x.shape
+    geo = {}
+
+    def body(tape, xv, yv):
+        plan.sn.run(blk.training, tape.record)
+        wp, wd, cs = plan.sn.colscales[0]
+        gbv = conv(tape, yv, None, n, 1, 1, 1, out_dtype=torch.float32, out_shape=(n, plan.gb_cols),
+                   grouped=(wp, wd, cs, plan.gb_cols, plan.gb_layers))
+        dgb = None
+        if tape.record:
+            dgb = torch.zeros_like(gbv.t)
+            gbv.g = dgb
+        out, ho, wo = _gblock(tape, blk, _to_nhwc(tape, xv), n, hh, ww, plan, gbv.t, dgb, blk.training)
+        geo["hw"] = (ho, wo)
+        return [_to_nchw(tape, out, n, ho, wo)]
+    return run_net(body, [x, y], list(blk.parameters()))
 
 
+@on_tensor_device
 def module_dblock(blk, x):
     x = _plain(x)
     L.require_device(x)
@@ -1459,6 +1652,7 @@ def module_dblock(blk, x):
     return run_net(body, [x], list(blk.parameters()))
 
 
+@on_tensor_device
 def module_attention(m, x):
     x = _plain(x)
     L.require_device(x)
@@ -1472,6 +1666,7 @@ def module_attention(m, x):
     return run_net(body, [x], list(m.parameters()))
 
 
+@on_tensor_device
 def module_rrm(blocks, final_norm, x):
     x = _plain(x)
     L.require_device(x)
@@ -1491,6 +1686,7 @@ def module_rrm(blocks, final_norm, x):
     return run_net(body, [x.reshape(b_ * s, e)], params).view(b_, s, e)
 
 
+@on_tensor_device
 def module_mha(m, x, return_attention=False):
     x = _plain(x)
     L.require_device(x)
@@ -1510,11 +1706,37 @@ def module_mha(m, x, return_attention=False):
     return (o, keep["att"]) if return_attention else o
 
 
+@on_tensor_device
 def module_sdp(q, k, v):
-    """RRM.scaled_dot_product on (B, h, 40, d) tensors (forward values + attention map)."""
+    """RRM.scaled_dot_product on (B, h, 40, d) tensors: (values, attention map), differentiable w.r.t.
+    q, k, v through the values (RRM.py:10-16; the map is returned for inspection, as get_attention_maps
+    uses it, and carries no gradient)."""
     q, k, v = _plain(q), _plain(k), _plain(v)
     L.require_device(q)
     b_, hds, s, d = q.shape
-    qkv = torch.cat([q, k, v], -1).permute(0, 2, 1, 3).reshape(b_ * s, hds * 3 * d).contiguous()
-    val, att = mha_core(Tape(False), Var(qkv, need=False), b_, s, hds, d)
-    return val.t.view(b_, s, hds, d).permute(0, 2, 1, 3), att
+    if s != IMGS or k.shape != q.shape or v.shape != q.shape:
+        raise NotImplementedError("the RRM kernels attend over the 40 sensors of an event with equal q/k/v widths")
+    keep = {}
+
+    def body(tape, qv, kv, vv):
+        # the kernel reads the module's own layout: rows (B*S), columns [head][q | k | v]
+        qkv = torch.cat([qv.t, kv.t, vv.t], -1).permute(0, 2, 1, 3).reshape(b_ * s, hds * 3 * d).contiguous()
+        pk = Var(qkv)
+        val, att = mha_core(tape, pk, b_, s, hds, d)
+        keep["att"] = att
+        out = Var(val.t.view(b_, s, hds, d).permute(0, 2, 1, 3).contiguous())
+        if tape.record:
+            def bw_in():  # (runs last) split d(qkv) back into the three inputs
+                if pk.g is None:
+                    return
+                g = pk.g.view(b_, s, hds, 3 * d).permute(0, 2, 1, 3)
+                qv.g, kv.g, vv.g = (g[..., :d].contiguous(), g[..., d:2 * d].contiguous(), g[..., 2 * d:].contiguous())
+
+            def bw_out():  # (runs first) gradient of the returned (B,h,S,d) values -> kernel layout
+                if out.g is not None:
+                    val.g = out.g.permute(0, 2, 1, 3).reshape(b_ * s, hds * d).contiguous()
+            tape.nodes.insert(0, bw_in)
+            tape.add(bw_out)
+        return [out]
+    vals = run_net(body, [q, k, v], [])
+    return vals, keep["att"]

@@ -110,9 +110,30 @@ class Attention(nn.Module):
         return E.module_attention(self, x)
 
 
+def fused_bn(x, mean, var, gain=None, bias=None, eps=1e-5):
+    """x * rsqrt(var + eps) * gain - (mean * rsqrt(var + eps) * gain - bias) with per-channel mean / var
+    (layers.py:505-517).  gain / bias: None, (1,C,1,1) or per-sample (N,C,1,1); gradients flow to x, gain and
+    bias (mean / var are treated as given statistics, which is how myBN's eval branch uses this function)."""
+    c = x.shape[1]
+    return E.bn_functional(x, gain, bias, stored_mean=mean.detach().reshape(c).float().contiguous(),
+                           stored_var=var.detach().reshape(c).float().contiguous(), training=False, mode=0, eps=eps,
+                           momentum=0.0)
+
+
+def manual_bn(x, gain=None, bias=None, return_mean_var=False, eps=1e-5):
+    """Batch-norm from mean-of-squares statistics, differentiable through them (layers.py:522-542).
+    With return_mean_var also (mean, biased var) -- (C,) for one event, (E, C) for a batch of E events."""
+    out = E.bn_functional(x, gain, bias, stored_mean=None, stored_var=None, training=True, mode=1, eps=eps,
+                          momentum=0.0, want_stats=return_mean_var)
+    if return_mean_var:
+        y, m, v = out
+        return y, m.squeeze(0), v.squeeze(0)
+    return out
+
+
 class myBN(nn.Module):
-    """Buffers of the reference's hand-written BN (layers.py:547-599).  Only reachable with
-    mybn=True, which the shipped config never sets; kept so state dicts load."""
+    """The reference's hand-written BN with standing statistics (layers.py:547-599): running variance is the
+    BIASED batch variance, accumulate_standing sums the statistics and counts the calls, eval divides."""
 
     def __init__(self, num_channels, eps=1e-5, momentum=0.1):
         super().__init__()
@@ -128,7 +149,7 @@ class myBN(nn.Module):
         self.accumulation_counter[:] = 0
 
     def forward(self, x, gain, bias):
-        raise NotImplementedError("mybn=True is outside the built hot path (config.json:24 mybn=false)")
+        return E.module_mybn(self, x, gain, bias)
 
 
 class ccbn(nn.Module):
@@ -148,8 +169,11 @@ class ccbn(nn.Module):
         elif norm_style in ("bn", "in"):
             self.register_buffer("stored_mean", torch.zeros(output_size))
             self.register_buffer("stored_var", torch.ones(output_size))
-        if mybn or norm_style != "bn":
-            raise NotImplementedError("built: norm_style='bn', mybn=False (the shipped config)")
+        if cross_replica:
+            raise NotImplementedError("cross_replica needs the sync_batchnorm package the reference does not ship "
+                                      "(layers.py:647-648)")
+        if norm_style != "bn":
+            raise NotImplementedError("built: norm_style='bn' (config.json:18)")
 
     def forward(self, x, y):
         return E.module_ccbn(self, x, y)
@@ -167,10 +191,14 @@ class bn(nn.Module):
         self.gain = nn.Parameter(torch.ones(output_size), requires_grad=True)
         self.bias = nn.Parameter(torch.zeros(output_size), requires_grad=True)
         self.eps, self.momentum, self.cross_replica, self.mybn = eps, momentum, cross_replica, mybn
+        if cross_replica:
+            raise NotImplementedError("cross_replica needs the sync_batchnorm package the reference does not ship "
+                                      "(layers.py:720-721)")
         if mybn:
-            raise NotImplementedError("built: mybn=False (the shipped config)")
-        self.register_buffer("stored_mean", torch.zeros(output_size))
-        self.register_buffer("stored_var", torch.ones(output_size))
+            self.bn = myBN(output_size, self.eps, self.momentum)
+        else:
+            self.register_buffer("stored_mean", torch.zeros(output_size))
+            self.register_buffer("stored_var", torch.ones(output_size))
 
     def forward(self, x, y=None):
         return E.module_bn(self, x)

@@ -69,10 +69,26 @@ class EMA:
             torch._foreach_add_([d for d, _ in fl], [s for _, s in fl], alpha=1 - decay)
 
 
+def check_config(config):
+    """This step function is the shipped configuration's path through train_fns.train (Contra head, split_D,
+    toggled grads, one D step, no accumulation, no consistency regularisation).  Any other setting changes the
+    objective the reference would optimise, so it is refused here instead of silently ignored; the reference's
+    own train_fns.py runs on the drop-in modules for those."""
+    want = {"num_D_steps": 1, "num_D_accumulations": 1, "num_G_accumulations": 1, "toggle_grads": True,
+            "conditional_strategy": "Contra", "split_D": True, "Con_reg": False}
+    bad = {k: config[k] for k, v in want.items() if k in config and config[k] != v}
+    if bad:
+        raise NotImplementedError("make_train_step is built for %s; got %s -- use the reference's train_fns.py on "
+                                  "the drop-in modules for other settings" % (want, bad))
+
+
 def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
     """Returns train(x, y) -> dict of the five floats train_fns.train returns.
     grad_hook(net) is called after each backward (the data-parallel all-reduce point)."""
+    check_config(config)
     contra = losses.Conditional_Contrastive_loss(None, config["batch_size"], config["pos_collected_numerator"])
+    use_unif = bool(config.get("Uniformity_loss", True))
+    use_iea = bool(config.get("IEA_loss", True))
     state = state if state is not None else {"itr": 0}
     g_params, d_params = list(G.parameters()), list(D.parameters())  # walked once, not ten times per step
     g_black = list(G.shared.parameters())
@@ -89,8 +105,10 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
                                             diff_aug=config["diff_aug"])
         l_real, l_fake = losses.loss_hinge_dis(d_fake, d_real)
         d_loss = l_real + l_fake + config["contra_lambda"] * contra(er, pr, None, y, t, 0)
-        unif_d = losses.unif_loss(er)
-        d_loss = d_loss + config["unif_lambda"] * unif_d
+        unif_d = torch.zeros((), device=d_loss.device)
+        if use_unif:  # train_fns.py:122-124
+            unif_d = losses.unif_loss(er)
+            d_loss = d_loss + config["unif_lambda"] * unif_d
         d_loss.backward()
         if grad_hook is not None:
             grad_hook(D)
@@ -106,8 +124,12 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
         z = z_.sample_()
         pf, ef, d_fake = GD(z, y, contra=True, train_G=True, split_D=True, diff_aug=config["diff_aug"])
         g_loss = losses.loss_hinge_gen(d_fake) + config["contra_lambda"] * contra(ef, pf, None, y, t, 0)
-        iea_l = losses.IEA_loss(ef, er)
-        g_loss = g_loss + config["IEA_lambda"] * iea_l + config["unif_lambda"] * losses.unif_loss(ef)
+        iea_l = torch.zeros((), device=g_loss.device)
+        if use_iea:  # train_fns.py:169-176: the G uniformity term sits INSIDE the IEA branch
+            iea_l = losses.IEA_loss(ef, er)
+            g_loss = g_loss + config["IEA_lambda"] * iea_l
+            if use_unif:
+                g_loss = g_loss + config["unif_lambda"] * losses.unif_loss(ef)
         g_loss.backward()
         if grad_hook is not None:
             grad_hook(G)

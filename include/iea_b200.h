@@ -161,14 +161,19 @@ int iea_residual_bwd(const void* g, int g_dtype, int g_ld, int64_t n, int h, int
 /* stand-alone statistics partials: [events][tiles][c][2] */
 int iea_bn_stats(const void* x, int x_dtype, int x_ld, int64_t rows, int rows_per_event, int c,
                  int tiles_per_event, float* partials, iea_stream_t stream);
-/* partials -> batch mean / rstd per (event, c) (biased variance), running-stat update
- * (momentum, unbiased variance) when training; eval uses the stored statistics.
- * scale[n][c] = rstd*(gain_add + gain[n*gain_ld + c]); shift = bias - mean*scale. */
+/* partials -> batch mean / rstd per (event, c) (biased variance), running-stat update when
+ * training; eval (mode 0) uses the stored statistics.
+ * mode bits: 1 = batch statistics + F.batch_norm running update (momentum, UNBIASED variance,
+ * layers.py:664-673); 1|2 = myBN running update (momentum, biased variance, layers.py:585-592);
+ * 1|4 = myBN standing statistics (stored += batch statistic, layers.py:579-582).
+ * scale[n][c] = rstd*(gain_add + gain[n*gain_ld + c]); shift = bias - mean*scale.
+ * ticket: caller-owned, ceil(c/8) zero-initialised counters private to this layer (self-resetting);
+ * with it the training path is ONE launch, without it (NULL) three. */
 int iea_bn_finalize(const float* partials, int events, int tiles_per_event, int64_t count_per_event,
                     int imgs_per_event, int c, const float* gain, int64_t gain_ld, float gain_add,
                     const float* bias, int64_t bias_ld, float* stored_mean, float* stored_var,
-                    int training, float momentum, float eps, float* mean_out, float* rstd_out,
-                    float* scale, float* shift, iea_stream_t stream);
+                    int mode, float momentum, float eps, float* mean_out, float* rstd_out,
+                    float* scale, float* shift, unsigned int* ticket, iea_stream_t stream);
 /* backward: (dscale, dshift)[n][c] -> dgain[n][c], dbias[n][c] (pixel-stride ld, beta accumulate)
  * and the statistics gradients ds1, ds2 [events][c] consumed by iea_conv_out_bwd. */
 int iea_bn_finalize_bwd(const float* dscale, const float* dshift, const float* scale,
@@ -257,6 +262,10 @@ int iea_loss_hinge_dis_bwd(const float* fake, const float* real, const float* do
 /* out[0] = scale * mean(x) (loss_hinge_gen: scale = -1) and its backward dx[i] = dout*scale/n */
 int iea_loss_mean(const float* x, int64_t n, float scale, float* out, iea_stream_t stream);
 int iea_loss_mean_bwd(const float* dout, int64_t n, float scale, float* dx, iea_stream_t stream);
+/* loss.py:41-44 l2_loss: out[0] = mean((a-b)^2); backward da = 2(a-b) dout/n, db = -da (either may be NULL) */
+int iea_loss_l2(const float* a, const float* b, int64_t n, float* out, iea_stream_t stream);
+int iea_loss_l2_bwd(const float* a, const float* b, const float* dout, int64_t n, float* da, float* db,
+                    iea_stream_t stream);
 int iea_loss_contrastive_fwd(const float* embed, const float* proxy, int events, int seq, int dim,
                              float temperature, float margin, float* loss, float* saved /* events*(2*seq*seq+4*seq+1) */,
                              iea_stream_t stream);

@@ -5,6 +5,8 @@ import os
 import pytest
 import torch
 
+from iea_gan_b200 import noise
+
 pytestmark = pytest.mark.gpu
 
 
@@ -60,15 +62,9 @@ def test_diffaugment_vs_golden_and_grad(golden_fwd):
         torch.manual_seed(seed)
         d = O.diffaug_draws(*shape)  # CPU stream, as in the golden run
         seq = [d["brightness"], d["saturation"], d["contrast"], d["tx"], d["ty"], d["ox"], d["oy"]]
-        it = iter(seq)
-        real_rand, real_randint = torch.rand, torch.randint
-        try:
-            torch.rand = lambda *a, **k: next(it).cuda()
-            torch.randint = lambda *a, **k: next(it).cuda()
+        with noise.replay(seq):
             xg = x.cuda().requires_grad_(True)
             out = DiffAugment(xg, policy="color,translation,cutout")
-        finally:
-            torch.rand, torch.randint = real_rand, real_randint
         assert rel(out, golden_fwd[key_out]) < 1e-6
         g = torch.randn_like(out)
         out.backward(g)
@@ -140,22 +136,14 @@ def test_train_step_vs_unmodified_train_fns(small_cfg, golden_step, adt):
             rd = torch.randn(40, cfg["rdof_dim"])
             d = O.diffaug_draws(40, 64, 64)
             draws.append((z, rd, [d["brightness"], d["saturation"], d["contrast"], d["tx"], d["ty"], d["ox"], d["oy"]]))
-        phase = {"i": -1}
+        zs = iter([d[0] for d in draws])
 
         class Z:
             def sample_(self):
-                phase["i"] += 1
-                phase["it"] = iter(draws[phase["i"]][2])
-                return draws[phase["i"]][0].cuda()
-        real = (torch.randn, torch.rand, torch.randint)
-        try:
-            torch.randn = lambda *a, **k: draws[phase["i"]][1].cuda() if (len(a) == 2 and a[1] == cfg["rdof_dim"]) else real[0](*a, **k)
-            torch.rand = lambda *a, **k: next(phase["it"]).cuda()
-            torch.randint = lambda *a, **k: next(phase["it"]).cuda()
+                return next(zs).cuda()
+        with noise.replay([t for _, rd, aug in draws for t in [rd] + aug]):  # per phase: rdof, then the 7 DiffAugment draws
             train = make_train_step(G, D, GD, Z(), cfg)
             losses = train(golden_step["x"].cuda(), torch.arange(40, device="cuda"))
-        finally:
-            torch.randn, torch.rand, torch.randint = real
         ltol, gtol, ftol = (1e-3, 1e-2, 2e-2) if adt == "fp32" else (3e-2, 0.15, 0.2)
         for k, v in golden_step["losses"].items():
             assert abs(losses[k] - v) < ltol * max(1.0, abs(v)), (k, losses[k], v)

@@ -1,0 +1,249 @@
+"""Correctness AT THE BENCHMARKED CONFIGURATIONS (BASELINE.json configs 1-3: shipped widths, 256x256):
+
+  * a full G+D train step on two events against the fp32 CPU oracle -- the five losses, the gradient of every
+    parameter of G (the full-size Generator backward) and of D, the buffers (fp32 activations tight, bf16 stated);
+  * the E = 8 train step bench.py times and the E = 16 sampling batch: one batched call must equal the same
+    events run one at a time on the GPU (per-event batch-norm groups, the fused finalize's ticket path, per-event
+    loss means, grouped SN backward) -- the size-independent property that extends the oracle pin from E <= 2 to
+    the benchmarked batch sizes without minutes of CPU time;
+  * a 20-step loss trajectory, bf16 against fp32 activations, on the small configuration: the justification
+    for accepting the bf16 gradient tolerances.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def draws_for(cfg, seed, rows, hh, ww):
+    from oracle import iea_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    ph = []
+    for _ in range(2):
+        z = torch.randn(rows, cfg["dim_z"], generator=g)
+        rd = torch.randn(rows, cfg["rdof_dim"], generator=g)
+        ph.append((z, rd, O.diffaug_draws(rows, hh, ww, generator=g)))
+    return ph
+
+
+def replay_list(phases, rows=None):
+    out = []
+    for _, rd, d in phases:
+        s = slice(None) if rows is None else rows
+        out.append(("randn", rd[s]))
+        out += [("rand", d[k][s]) for k in ("brightness", "saturation", "contrast")]
+        out += [("randint", d[k][s]) for k in ("tx", "ty", "ox", "oy")]
+    return out
+
+
+class FixedZ:
+    def __init__(self, phases, rows=None):
+        self.it = iter([p[0] if rows is None else p[0][rows] for p in phases])
+
+    def sample_(self):
+        return next(self.it).cuda()
+
+
+def fresh_nets(cfg, seed=0):
+    import iea_gan_b200 as P
+    torch.manual_seed(seed)
+    G, D = P.Generator(**cfg), P.Discriminator(**cfg)
+    with torch.no_grad():
+        for m in D.modules():
+            if hasattr(m, "gamma") and isinstance(m.gamma, torch.nn.Parameter):
+                m.gamma.fill_(0.5)  # the attention block must contribute
+    sg = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    return G.cuda().train(), D.cuda().train(), sg, sd
+
+
+def gpu_step(cfg, phases, x, y, adt, rows=None, nets=None):
+    import iea_gan_b200 as P
+    from iea_gan_b200 import noise
+    from iea_gan_b200.train_step import make_train_step
+    os.environ["IEA_ACT_DTYPE"] = adt
+    try:
+        G, D, _, _ = nets if nets is not None else fresh_nets(cfg)
+        n = x.shape[0]
+        train = make_train_step(G, D, P.G_D(G, D), FixedZ(phases, rows), dict(cfg, batch_size=n))
+        with noise.replay(replay_list(phases, rows)):
+            losses = train(x.cuda(), y.cuda())
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)
+    return G, D, losses
+
+
+@pytest.fixture(scope="module")
+def oracle_two_events():
+    """fp32 CPU oracle of one full-size G+D step on two events (about a minute of host time), shared by both dtypes."""
+    from iea_gan_b200.default_config import shipped_config
+    from oracle import iea_oracle as O
+    import iea_gan_b200 as P
+    cfg = shipped_config(H_base=1, device="cuda", clip_norm=1e9)
+    rows = 80
+    phases = draws_for(cfg, 401, rows, 256, 256)
+    torch.manual_seed(402)
+    x = torch.rand(rows, 1, 256, 256) * 2 - 1
+    x[x < 0.6] = -1.0  # sparse, PXD-like occupancy
+    y = torch.arange(40).repeat(2)
+    torch.manual_seed(0)
+    ccfg = dict(cfg, device="cpu")
+    Gc, Dc = P.Generator(**ccfg), P.Discriminator(**ccfg)
+    with torch.no_grad():
+        for m in Dc.modules():
+            if hasattr(m, "gamma") and isinstance(m.gamma, torch.nn.Parameter):
+                m.gamma.fill_(0.5)
+    sg = {k: v.detach().clone() for k, v in Gc.state_dict().items()}
+    sd = {k: v.detach().clone() for k, v in Dc.state_dict().items()}
+    nz = dict(z_d=phases[0][0], rdof_d=phases[0][1], aug_d=phases[0][2], z_g=phases[1][0], rdof_g=phases[1][1],
+              aug_g=phases[1][2])
+    torch.set_num_threads(os.cpu_count() or 1)
+    want = O.train_step(sg, sd, ccfg, x, y, nz)  # no optimizers: D is not stepped between the phases (see below)
+    return cfg, phases, x, y, sg, sd, want
+
+
+@pytest.mark.parametrize("adt", ["fp32", "bf16"])
+def test_full_size_train_step_two_events_vs_oracle(oracle_two_events, adt):
+    """Tolerances.  fp32 activations: losses 1e-3, every parameter gradient 2e-2 relative L2 (a handful of ReLU
+    masks flip at fp32 rounding level in a 100+-layer G->D chain), buffers 1e-4.  bf16 activations / gradients:
+    losses 3e-2, gradient NORMS within 15 %, full gradients within 30 % relative L2 for tensors above the noise
+    floor (G's gradients pass D backward, DiffAugment and G backward in bf16: ~150 rounded layers, mask flips not
+    averaged for the small tensors), buffers 3e-2.
+    D's optimizer is given lr = 0 so that both sides run the G phase on the same D weights."""
+    cfg, phases, x, y, sg, sd, want = oracle_two_events
+    G, D, _, _ = fresh_nets(cfg)
+    for grp in D.optim.param_groups:
+        grp["lr"] = 0.0
+    G, D, got = gpu_step(cfg, phases, x, y, adt, nets=(G, D, None, None))
+    ltol = 1e-3 if adt == "fp32" else 3e-2
+    for k, v in want.items():
+        assert abs(got[k] - v) < ltol * max(1.0, abs(v)), (k, got[k], v)
+    bad, worst = [], 0.0
+    for tag, net, ref in (("G", G, sg), ("D", D, sd)):
+        for k, p in net.named_parameters():
+            rg = ref[k].grad
+            if float(rg.norm()) < 1e-7:
+                continue  # exactly-zero reference gradient (conv bias in front of a batch-norm)
+            r = rel(p.grad, rg)
+            nr = abs(float(p.grad.norm()) - float(rg.norm())) / float(rg.norm())
+            worst = max(worst, r)
+            if adt == "fp32" and r > 2e-2:
+                bad.append((tag, k, r))
+            if adt == "bf16" and (nr > 0.15 or r > 0.30):
+                bad.append((tag, k, r, nr))
+    assert not bad, (len(bad), bad[:8])
+    btol = 1e-4 if adt == "fp32" else 3e-2
+    for net, ref in ((G, sg), (D, sd)):
+        st = net.state_dict()
+        for k in ref:
+            if k.endswith(("u0", "sv0", "stored_mean", "stored_var")):
+                assert rel(st[k].float(), ref[k].float()) < btol, k
+    print("full-size 2-event step (%s): worst parameter-gradient rel-L2 %.3g" % (adt, worst))
+
+
+def test_benchmarked_batches_equal_per_event_runs():
+    """E = 8 train step (BASELINE config 2/3 as bench.py runs it, bf16): gradients and losses of ONE batched
+    step == mean over 8 single-event steps started from the same weights and spectral-norm vectors.
+    E = 16 sampling: one batched forward == 16 single-event forwards.  Same arithmetic per event on both sides
+    (same bf16 rounding points), so only fp32 summation order differs: 2e-3 on images, 1e-2 on gradients."""
+    from iea_gan_b200.default_config import shipped_config
+    from iea_gan_b200 import noise
+    cfg = shipped_config(H_base=1, device="cuda", clip_norm=1e9)
+    E_ = 8
+    rows = 40 * E_
+    phases = draws_for(cfg, 501, rows, 256, 256)
+    torch.manual_seed(502)
+    x = torch.rand(rows, 1, 256, 256) * 2 - 1
+    y = torch.arange(40).repeat(E_)
+
+    def zero_lr(G, D):
+        for o in (G.optim, D.optim):
+            for grp in o.param_groups:
+                grp["lr"] = 0.0
+    G, D, _, _ = fresh_nets(cfg)
+    zero_lr(G, D)
+    state0 = ({k: v.clone() for k, v in G.state_dict().items()}, {k: v.clone() for k, v in D.state_dict().items()})
+    G, D, got = gpu_step(cfg, phases, x, y, "bf16", nets=(G, D, None, None))
+    gb = {("G", k): p.grad.clone() for k, p in G.named_parameters()}
+    gb.update({("D", k): p.grad.clone() for k, p in D.named_parameters()})
+    acc, lsum = {k: torch.zeros_like(v) for k, v in gb.items()}, {}
+    for e in range(E_):
+        G.load_state_dict(state0[0]); D.load_state_dict(state0[1])  # same weights, same u0 for every event
+        G.optim.zero_grad(); D.optim.zero_grad()
+        sl = slice(40 * e, 40 * e + 40)
+        _, _, l1 = gpu_step(cfg, phases, x[sl], y[sl], "bf16", rows=sl, nets=(G, D, None, None))
+        for k, p in list(G.named_parameters()):
+            acc[("G", k)] += p.grad / E_
+        for k, p in list(D.named_parameters()):
+            acc[("D", k)] += p.grad / E_
+        for k, v in l1.items():
+            lsum[k] = lsum.get(k, 0.0) + v / E_
+    for k, v in lsum.items():
+        assert abs(got[k] - v) < 2e-3 * max(1.0, abs(v)), (k, got[k], v)
+    bad = [(k, rel(gb[k], acc[k])) for k in gb if float(acc[k].norm()) > 1e-6 and rel(gb[k], acc[k]) > 1e-2]
+    assert not bad, (len(bad), bad[:8])
+    # ---- sampling, 16 events
+    rows = 640
+    g = torch.Generator().manual_seed(503)
+    z, rd = torch.randn(rows, cfg["dim_z"], generator=g).cuda(), torch.randn(rows, cfg["rdof_dim"], generator=g)
+    y = torch.arange(40).repeat(16).cuda()
+    G.load_state_dict(state0[0])
+    with torch.no_grad(), noise.replay([rd]):
+        img = G(z, y)
+    for e in (0, 7, 15):
+        G.load_state_dict(state0[0])
+        sl = slice(40 * e, 40 * e + 40)
+        with torch.no_grad(), noise.replay([rd[sl]]):
+            one = G(z[sl], y[sl])
+        assert rel(img[sl], one) < 2e-3, e
+
+
+def test_loss_trajectory_bf16_tracks_fp32(small_cfg):
+    """20 optimizer steps from the same seed with bf16 and with fp32 activations (same noise: the CUDA generator is
+    re-seeded): the five reported losses must track each other -- max deviation over the trajectory <= 5 % of the
+    loss scale (|value| floor 1.0), and the final parameter vectors stay within 2 % of each other relative to the
+    distance travelled.  This is what a user of the bf16 path accepts in place of per-gradient agreement."""
+    import iea_gan_b200 as P
+    from iea_gan_b200.train_step import make_train_step, NormalNoise
+    cfg = dict(small_cfg, device="cuda")
+    runs = {}
+    for adt in ("fp32", "bf16"):
+        os.environ["IEA_ACT_DTYPE"] = adt
+        try:
+            torch.manual_seed(0)
+            G, D = P.Generator(**cfg).cuda().train(), P.Discriminator(**cfg).cuda().train()
+            p0 = torch.cat([p.detach().reshape(-1) for p in list(G.parameters()) + list(D.parameters())]).clone()
+            torch.manual_seed(77)
+            torch.cuda.manual_seed(77)
+            train = make_train_step(G, D, P.G_D(G, D), NormalNoise(40, cfg["dim_z"], "cuda"), cfg)
+            y = torch.arange(40, device="cuda")
+            traj = []
+            for i in range(20):
+                x = torch.rand(40, 1, 64, 64, device="cuda") * 2 - 1
+                traj.append(train(x, y))
+            p1 = torch.cat([p.detach().reshape(-1) for p in list(G.parameters()) + list(D.parameters())])
+            runs[adt] = (traj, p0, p1)
+        finally:
+            os.environ.pop("IEA_ACT_DTYPE", None)
+    (ta, p0, pa), (tb, _, pb) = runs["fp32"], runs["bf16"]
+    dev = max(abs(a[k] - b[k]) / max(1.0, abs(a[k])) for a, b in zip(ta, tb) for k in a)
+    assert dev < 5e-2, dev
+    assert all(v == v for t in tb for v in t.values())
+    travelled = float((pa - p0).norm())
+    assert float((pa - pb).norm()) < 0.02 * float(p0.norm()) and travelled > 0
+    print("trajectory: max loss deviation %.3g, |p_bf16 - p_fp32| / |p_fp32 - p_0| = %.3g"
+          % (dev, float((pa - pb).norm()) / travelled))

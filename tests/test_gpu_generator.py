@@ -4,6 +4,8 @@ import os
 import pytest
 import torch
 
+from iea_gan_b200 import noise
+
 pytestmark = pytest.mark.gpu
 
 
@@ -39,13 +41,8 @@ def test_generator_train_mode_vs_golden(small_cfg, golden_fwd, adt, tol):
         rd = torch.randn(40, cfg["rdof_dim"])  # the CPU stream's next draw, as in the golden run
         import iea_gan_b200.engine as E
         y = torch.arange(40, device="cuda")
-        with torch.no_grad():
-            real_randn = torch.randn
-            try:
-                torch.randn = lambda *a, **k: rd.cuda() if (len(a) == 2 and a[1] == cfg["rdof_dim"]) else real_randn(*a, **k)
-                img = G(z, y)
-            finally:
-                torch.randn = real_randn
+        with torch.no_grad(), noise.replay([("randn", rd)]):  # the CPU stream's rdof draw, handed to the forward
+            img = G(z, y)
         assert img.shape == (40, 1, 64, 64)
         assert rel(img, golden_fwd["g_train_img"]) < tol
         assert rel(G.linear.u0, golden_fwd["g_u0_linear_after"]) < 1e-4
@@ -53,6 +50,34 @@ def test_generator_train_mode_vs_golden(small_cfg, golden_fwd, adt, tol):
         btol = 1e-4 if adt == "fp32" else 2e-2
         assert rel(G.blocks[0][0].bn1.stored_mean, golden_fwd["g_bn_mean_after"]) < btol
         assert rel(G.blocks[0][0].bn1.stored_var, golden_fwd["g_bn_var_after"]) < btol
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)
+
+
+@pytest.mark.parametrize("adt,tol", [("fp32", 2e-4), ("bf16", 4e-2)])
+def test_generator_eval_mode_vs_golden(small_cfg, golden_fwd, adt, tol):
+    """G.eval() (train.py:190-194 G_eval_mode): stored batch-norm statistics, and NO buffer is written -- the
+    golden run did one training forward (which moved u0 / sv0 / running statistics) and then this eval forward."""
+    os.environ["IEA_ACT_DTYPE"] = adt
+    try:
+        cfg = dict(small_cfg, device="cuda")
+        G, _ = build_G(cfg)
+        G.train()
+        torch.manual_seed(101)
+        z = torch.randn(40, cfg["dim_z"]).cuda()
+        rd = torch.randn(40, cfg["rdof_dim"])
+        y = torch.arange(40, device="cuda")
+        with torch.no_grad(), noise.replay([("randn", rd)]):
+            G(z, y)
+        torch.manual_seed(102)
+        rd2 = torch.randn(40, cfg["rdof_dim"])
+        G.eval()
+        before = {k: v.clone() for k, v in G.state_dict().items()}
+        with torch.no_grad(), noise.replay([("randn", rd2)]):
+            img = G(z, y)
+        assert rel(img, golden_fwd["g_eval_img"]) < tol
+        after = G.state_dict()
+        assert all(torch.equal(before[k], after[k]) for k in before), "eval mode wrote a buffer"
     finally:
         os.environ.pop("IEA_ACT_DTYPE", None)
 
@@ -71,12 +96,8 @@ def test_generator_multi_event_vs_oracle(small_cfg):
         y = torch.arange(40).repeat(2)
         with torch.no_grad():
             ref = O.generator_forward(sd, cfg, z, y, rd, training=True)
-            real_randn = torch.randn
-            try:
-                torch.randn = lambda *a, **k: rd.cuda() if (len(a) == 2 and a[1] == cfg["rdof_dim"]) else real_randn(*a, **k)
+            with noise.replay([("randn", rd)]):
                 img = G(z.cuda(), y.cuda())
-            finally:
-                torch.randn = real_randn
         assert rel(img, ref) < 2e-4
         assert rel(G.blocks[3][0].bn2.stored_var, sd["blocks.3.0.bn2.stored_var"]) < 1e-4
     finally:
@@ -92,13 +113,8 @@ def test_generator_hbase3_vs_golden(small_cfg, golden_fwd):
     torch.manual_seed(108)
     z = torch.randn(40, cfg["dim_z"])
     rd = torch.randn(40, cfg["rdof_dim"])
-    real_randn = torch.randn
-    try:
-        torch.randn = lambda *a, **k: rd.cuda() if (len(a) == 2 and a[1] == cfg["rdof_dim"]) else real_randn(*a, **k)
-        with torch.no_grad():
-            img = G(z.cuda(), torch.arange(40, device="cuda"))
-    finally:
-        torch.randn = real_randn
+    with torch.no_grad(), noise.replay([("randn", rd)]):
+        img = G(z.cuda(), torch.arange(40, device="cuda"))
     assert img.shape == (40, 1, 64, 192)
     assert rel(img[:, :, ::4, ::4], golden_fwd["g3_img_sub"]) < 4e-2
     ms = golden_fwd["g3_mean_std"]
@@ -121,13 +137,8 @@ def test_full_size_sampling_vs_oracle_and_pixel_statistics():
     G = G.cuda().train()
     torch.manual_seed(11)
     z, rd, y = torch.randn(40, cfg["dim_z"]), torch.randn(40, cfg["rdof_dim"]), torch.arange(40)
-    real_randn = torch.randn
-    try:
-        torch.randn = lambda *a, **k: rd.cuda() if (len(a) == 2 and a[1] == cfg["rdof_dim"]) else real_randn(*a, **k)
-        with torch.no_grad():
-            img = G(z.cuda(), y.cuda())
-    finally:
-        torch.randn = real_randn
+    with torch.no_grad(), noise.replay([("randn", rd)]):
+        img = G(z.cuda(), y.cuda())
     with torch.no_grad():
         ref = O.generator_forward(sd, dict(cfg, device="cpu"), z, y, rd, training=True)
     assert img.shape == ref.shape == (40, 1, 256, 256)
