@@ -47,6 +47,10 @@ class ConvDesc(C.Structure):
                 ("stats", vp), ("impl", i32)]
 
 
+class MtChunk(C.Structure):
+    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("n", i32), ("tensor", i32)]
+
+
 class AugDraws(C.Structure):
     _fields_ = [("brightness", vp), ("contrast", vp), ("tx", vp), ("ty", vp), ("ox", vp), ("oy", vp),
                 ("cut_h", i32), ("cut_w", i32)]
@@ -107,6 +111,9 @@ _SIG = {
     "iea_loss_unif_fwd": [vp, i32, i32, i32, f32, vp, vp, vp],
     "iea_loss_unif_bwd": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
     "iea_adu_postprocess": [vp, i64, i32, i32, vp, vp],
+    "iea_mt_sqnorm": [vp, i32, vp, vp],
+    "iea_mt_adam": [vp, i32, vp, f32, f32, f32, f32, vp, vp, vp],
+    "iea_mt_lerp": [vp, i32, vp, vp],
 }
 
 _lib = None

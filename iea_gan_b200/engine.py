@@ -51,6 +51,7 @@ def conv_impl():
 LAUNCHES = [0]  # kernels launched through the C ABI (bench.py reports it)
 
 
+TRACE = None    # debugging aid: a list that receives (shape tag, output tensor) of every conv() call
 PROFILE = None  # tools/prof_layers.py sets this to a list: (name, tag, start event, end event) per C-ABI call
 
 
@@ -127,11 +128,13 @@ class Var:
 
 
 class Tape:
-    def __init__(self, record):
+    def __init__(self, record, flat=None):
         self.record = record
         self.nodes = []
         self.pgrads = {}
         self.sn_jobs = []  # deferred W/sigma backward of the layers of this pass: one grouped launch
+        self.flat = flat   # optim.FlatGrads of the owning net: parameter gradients are written in place
+        self.direct = set()
 
     def add(self, fn):
         if self.record:
@@ -143,10 +146,11 @@ class Tape:
         self.nodes = []
         self.flush_sn()
 
-    def sn_weight_bwd(self, gp, nsplit, layer, saved, dw):
-        """Queue dW = G/sigma - (<G,W>/sigma^2) u v^T for one layer (iea_sn_weight_bwd_grouped)."""
+    def sn_weight_bwd(self, gp, nsplit, layer, saved, dw, beta=0.0):
+        """Queue dW = beta*dW + G/sigma - (<G,W>/sigma^2) u v^T for one layer (iea_sn_weight_bwd_grouped)."""
         isg, u_, v_ = saved
-        self.sn_jobs.append((gp, nsplit, layer.weight, u_, v_, isg, layer.spectral, dw, layer.rows, layer.cin, layer.taps))
+        self.sn_jobs.append((gp, nsplit, layer.weight, u_, v_, isg, layer.spectral, dw, layer.rows, layer.cin, layer.taps,
+                             beta))
 
     def flush_sn(self):
         jobs, self.sn_jobs = self.sn_jobs, []
@@ -154,10 +158,10 @@ class Tape:
             return
         items = (L.SnBwdItem * len(jobs))()
         b0 = 0
-        for it, (gp, nsplit, w, u_, v_, isg, spectral, dw, rows, cin, taps) in zip(items, jobs):
+        for it, (gp, nsplit, w, u_, v_, isg, spectral, dw, rows, cin, taps, beta) in zip(items, jobs):
             nb = max(1, min(256, (rows * cin * taps + 1023) // 1024))
             it.gpart, it.w, it.u, it.v, it.inv_sigma, it.dw = ptr(gp), ptr(w), ptr(u_), ptr(v_), ptr(isg), ptr(dw)
-            it.nsplit, it.spectral, it.rows, it.cin, it.taps, it.beta = nsplit, spectral, rows, cin, taps, 0.0
+            it.nsplit, it.spectral, it.rows, it.cin, it.taps, it.beta = nsplit, spectral, rows, cin, taps, beta
             it.block0, it.nblocks = b0, nb
             b0 += nb
         dev = jobs[0][7].device
@@ -166,14 +170,56 @@ class Tape:
         K("iea_sn_weight_bwd_grouped", ptr(table), len(jobs), b0, ptr(_f32(b0, dev)), L.stream(), launches=2)
         self._sn_keep = (host, table)  # (stream-ordered allocators make dropping the job tensors safe once enqueued)
 
+    def galloc(self, param, accumulate_ok=False):
+        """Where a kernel should write the gradient of `param`: (tensor, beta).
+        With a flat gradient buffer (optim.FlatGrads) the tensor is the parameter's view of it: attached as
+        `param.grad` and overwritten (beta 0) when `param.grad` is None -- the first backward after
+        zero_grad() -- or accumulated into (beta 1, for kernels that can: accumulate_ok) when `param.grad`
+        already is that view (second Discriminator call of a pass, gradient accumulation).  Otherwise a fresh
+        tensor that pgrad() adds into the view / hands to autograd."""
+        fl = self.flat
+        if fl is not None:
+            k = id(param)
+            v = fl.views.get(k)
+            if v is not None:
+                g = param.grad
+                if g is None:
+                    param.grad = v
+                    self.direct.add(k)
+                    return v, 0.0
+                if g.data_ptr() == fl.ptrs[k]:
+                    self.direct.add(k)
+                    if accumulate_ok:
+                        if k in self.pgrads:
+                            self.flush_sn()  # (two queued jobs of one grouped launch must not write the same tensor)
+                        return v, 1.0
+        return torch.empty_like(param), 0.0
+
     def pgrad(self, param, g):
+        """Record gradient contribution g (the tensor a kernel wrote) of `param`."""
         k = id(param)
-        if k in self.pgrads:
-            self.flush_sn()  # (an accumulation reads the gradient a queued job has not written yet)
-            acc = self.pgrads[k]
-            K("iea_axpby", ptr(g), L.F32, 1.0, ptr(acc), L.F32, 1.0, ptr(acc), L.F32, g.numel(), L.stream())
-        else:
+        acc = self.pgrads.get(k)
+        if acc is None and k in self.direct:
+            acc = self.flat.views[k]
+            self.pgrads[k] = acc
+            if g.data_ptr() == acc.data_ptr():
+                return
+        elif acc is None:
+            fl = self.flat
+            if fl is not None and k in fl.views:
+                # a gradient produced outside galloc (small tensors: LayerNorm, bn gain / bias, gamma, embeddings):
+                # move it into the flat buffer so that EVERY gradient of the net lives there
+                tgt, beta = self.galloc(param, accumulate_ok=True)
+                if k in self.direct:
+                    K("iea_axpby", ptr(g), L.F32, 1.0, ptr(tgt), L.F32, beta, ptr(tgt), L.F32, g.numel(), L.stream())
+                    self.pgrads[k] = tgt
+                    return
             self.pgrads[k] = g
+            return
+        if g.data_ptr() == acc.data_ptr():
+            return  # written in place with beta = 1
+        self.flush_sn()  # (an accumulation reads the gradient a queued job has not written yet)
+        K("iea_axpby", ptr(g), L.F32, 1.0, ptr(acc), L.F32, 1.0, ptr(acc), L.F32, g.numel(), L.stream())
 
 
 def _accum_target(v):
@@ -189,6 +235,12 @@ def add_grad(v, g):
         v.g = g
     else:
         K("iea_axpby", ptr(g), dt(g), 1.0, ptr(v.g), dt(v.g), 1.0, ptr(v.g), dt(v.g), g.numel(), L.stream())
+
+
+def _scalar(device):
+    """0-d fp32 result tensor of a loss kernel (NOT a view of a 1-element buffer: callers accumulate losses in
+    place -- `G_loss += ...`, train_fns.py:168 -- which autograd forbids on a view made inside a custom Function)."""
+    return torch.empty((), dtype=torch.float32, device=device)
 
 
 def _f32(n, device):
@@ -451,6 +503,8 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
         st = torch.zeros((max(n // IMGS, 1) * slots, cout, 2), dtype=torch.float32, device=dev) if slots > 0 else None
         d.stats = ptr(st)
     K("iea_conv_fprop", C.byref(d), L.stream())
+    if TRACE is not None:
+        TRACE.append((_tag("iea_conv_fprop", (C.byref(d),)), yv.t, st))
     if stats:
         yv.bn = (st, slots, IMGS * h * w) if slots > 0 else None
     if not tape.record:
@@ -482,7 +536,7 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
               cout, ptr(geff), dt(geff), L.stream())
             g_t, g_ptr, g_ld = geff, geff.data_ptr(), cout
         need_db = bias is not None and bias.requires_grad
-        db = torch.empty(cout, dtype=torch.float32, device=dev) if need_db else None
+        db = tape.galloc(bias)[0] if need_db else None
         db_done = False
         if res is not None and res.need:
             rg, beta = _accum_target(res)
@@ -507,9 +561,9 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
             r0 = 0
             for l, (isg, u_, v_) in zip(wls, saved):
                 if l.weight.requires_grad:
-                    dw = torch.empty_like(l.weight)
+                    dw, beta = tape.galloc(l.weight, accumulate_ok=True)
                     gp = gpart if len(wls) == 1 else gpart[:, r0:r0 + l.rows].contiguous()
-                    tape.sn_weight_bwd(gp, nsplit, l, (isg, u_, v_), dw)
+                    tape.sn_weight_bwd(gp, nsplit, l, (isg, u_, v_), dw, beta)
                     tape.pgrad(l.weight, dw)
                 r0 += l.rows
         if need_db:
@@ -871,11 +925,15 @@ def _g_body(G, tape, z, y, rdof):
 # ------------------------------------------------------------------ autograd bridge
 class _NetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, body, n_in, *args):
-        tape = Tape(True)
+    def forward(ctx, body, n_in, owner, *args):
+        flat = None
+        if owner is not None and len(args) > n_in:
+            from .optim import FlatGrads
+            flat = FlatGrads.of(owner)
+        tape = Tape(True, flat)
         in_vars = [Var(a, need=bool(a.requires_grad)) for a in args[:n_in]]
         outs = body(tape, *in_vars)
-        ctx.tape, ctx.in_vars, ctx.outs, ctx.params, ctx.n_in = tape, in_vars, outs, args[n_in:], n_in
+        ctx.tape, ctx.in_vars, ctx.outs, ctx.params, ctx.n_in, ctx.owner = tape, in_vars, outs, args[n_in:], n_in, owner
         res = tuple(o.t for o in outs)
         return res if len(res) > 1 else res[0]
 
@@ -888,23 +946,40 @@ class _NetFn(torch.autograd.Function):
             if g is not None:
                 o.g = g.contiguous().to(o.t.dtype).view(o.t.shape)
         tape.backward()
-        gin = [v.g.view(v.t.shape) if (v.need and v.g is not None and ctx.needs_input_grad[2 + i]) else None
+        gin = [v.g.view(v.t.shape) if (v.need and v.g is not None and ctx.needs_input_grad[3 + i]) else None
                for i, v in enumerate(ctx.in_vars)]
-        gp = [tape.pgrads.get(id(p)) if ctx.needs_input_grad[2 + ctx.n_in + j] else None
+        # gradients written in place into the net's flat buffer (param.grad is already that view) are not handed to
+        # autograd a second time
+        gp = [tape.pgrads.get(id(p)) if (ctx.needs_input_grad[3 + ctx.n_in + j] and id(p) not in tape.direct) else None
               for j, p in enumerate(ctx.params)]
         ctx.tape = None
-        return (None, None) + tuple(gin) + tuple(gp)
+        owner = ctx.owner
+        if owner is not None and tape.direct:
+            sync = owner.__dict__.get("_iea_grad_sync")
+            if sync is not None:
+                sync.after_backward(owner)  # data-parallel: all-reduce the flat buffer at the end of this backward pass
+        return (None, None, None) + tuple(gin) + tuple(gp)
 
 
-def run_net(body, inputs, params):
-    """Execute body(tape, *in_vars) -> [Var] with a tape (under autograd) or without one."""
+def run_net(body, inputs, params, owner=None):
+    """Execute body(tape, *in_vars) -> [Var] with a tape (under autograd) or without one.
+    owner: the Generator / Discriminator whose parameters these are -- its gradients then live in one flat
+    buffer (optim.FlatGrads) that the kernels write in place."""
     record = torch.is_grad_enabled() and (any(a.requires_grad for a in inputs) or any(p.requires_grad for p in params))
     if record:
-        return _NetFn.apply(body, len(inputs), *inputs, *params)
+        return _NetFn.apply(body, len(inputs), owner, *inputs, *params)
     with torch.no_grad():
         outs = body(Tape(False), *[Var(a, need=False) for a in inputs])
     res = tuple(o.t for o in outs)
     return res if len(res) > 1 else res[0]
+
+
+def _params(net):
+    """Cached parameter list of a whole net (the module-tree walk costs ~1 ms per call)."""
+    ps = net.__dict__.get("_iea_params")
+    if ps is None:
+        ps = net.__dict__["_iea_params"] = list(net.parameters())
+    return ps
 
 
 def _plain(t, dtype=torch.float32):
@@ -927,7 +1002,7 @@ def generator_forward(G, z, y):
         img, hh, ww = _g_body(G, tape, zv, y, rdof)
         geo["hw"] = (hh, ww)
         return [img]
-    out = run_net(body, [z], list(G.parameters()))
+    out = run_net(body, [z], _params(G), owner=G)
     return out.view(n, 1, *geo["hw"])  # one channel: NHWC and NCHW coincide
 
 
@@ -1125,7 +1200,7 @@ def discriminator_forward(D, x, y):
 
     def body(tape, xv):
         return _d_body(D, tape, xv, y, hh, ww)
-    proxy, embed, out = run_net(body, [x4], list(D.parameters()))
+    proxy, embed, out = run_net(body, [x4], _params(D), owner=D)
     return proxy, embed, out.view(n)
 
 
@@ -1227,9 +1302,9 @@ def _mean_loss(x, scale):
     n = x.numel()
 
     def fwd(x):
-        out = _f32(1, x.device)
+        out = _scalar(x.device)
         K("iea_loss_mean", ptr(x), n, scale, ptr(out), L.stream())
-        return out[0], None
+        return out, None
 
     def bwd(saved, xs, g, need):
         dx = torch.empty_like(xs[0])
@@ -1252,9 +1327,9 @@ def loss_l2(a, b):
         raise ValueError("l2_loss: operands of %d and %d elements" % (n, b.numel()))
 
     def fwd(a, b):
-        out = _f32(1, a.device)
+        out = _scalar(a.device)
         K("iea_loss_l2", ptr(a), ptr(b), n, ptr(out), L.stream())
-        return out[0], None
+        return out, None
 
     def bwd(saved, xs, g, need):
         da, db = torch.empty_like(xs[0]), torch.empty_like(xs[1])
@@ -1270,11 +1345,11 @@ def loss_contrastive(embed, proxy, temperature, margin):
     ev, dim = _events(e), e.shape[1]
 
     def fwd(e, p):
-        out = _f32(1, e.device)
+        out = _scalar(e.device)
         saved = _f32(ev * (2 * IMGS * IMGS + 4 * IMGS + 1), e.device)
         K("iea_loss_contrastive_fwd", ptr(e), ptr(p), ev, IMGS, dim, temperature, margin, ptr(out), ptr(saved),
           L.stream(), launches=2)
-        return out[0], saved
+        return out, saved
 
     def bwd(saved, xs, g, need):
         de, dp = torch.empty_like(xs[0]), torch.empty_like(xs[1])
@@ -1291,10 +1366,10 @@ def loss_iea(k_f, k_r):
     ev, dim = _events(f), f.shape[1]
 
     def fwd(f, r):
-        out = _f32(1, f.device)
+        out = _scalar(f.device)
         saved = _f32(ev * (IMGS * IMGS + 1), f.device)
         K("iea_loss_iea_fwd", ptr(f), ptr(r), ev, IMGS, dim, ptr(out), ptr(saved), L.stream(), launches=2)
-        return out[0], saved
+        return out, saved
 
     def bwd(saved, xs, g, need):
         df = torch.empty_like(xs[0])
@@ -1310,10 +1385,10 @@ def loss_uniformity(x, t):
     ev, dim = _events(x), x.shape[1]
 
     def fwd(x):
-        out = _f32(1, x.device)
+        out = _scalar(x.device)
         saved = _f32(ev * (IMGS * IMGS + 2), x.device)
         K("iea_loss_unif_fwd", ptr(x), ev, IMGS, dim, t, ptr(out), ptr(saved), L.stream(), launches=2)
-        return out[0], saved
+        return out, saved
 
     def bwd(saved, xs, g, need):
         dx = torch.empty_like(xs[0])

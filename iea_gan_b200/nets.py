@@ -22,6 +22,7 @@ from . import sn_layers as layers
 from . import relational as RRM
 from . import engine as E
 from .augment import DiffAugment
+from .optim import FusedAdam
 
 # channel multipliers per output resolution: (in, out)
 _G_TABLE = {512: ([16, 16, 8, 8, 4, 2, 1], [16, 8, 8, 4, 2, 1, 1]),
@@ -85,7 +86,8 @@ def _ortho_init(net, style):
 
 def _make_optim(net, lr, b1, b2, eps, sched_version, kwargs):
     net.lr, net.B1, net.B2, net.adam_eps = lr, b1, b2, eps
-    net.optim = optim.Adam(params=net.parameters(), lr=lr, betas=(b1, b2), weight_decay=0, eps=eps)
+    # torch.optim.Adam's update (model.py:410-416, 858-864) as one multi-tensor kernel; same state_dict layout
+    net.optim = FusedAdam(params=net.parameters(), lr=lr, betas=(b1, b2), weight_decay=0, eps=eps)
     if sched_version == "CosAnnealLR":
         net.lr_sched = optim.lr_scheduler.CosineAnnealingLR(net.optim, T_max=kwargs["num_epochs"],
                                                             eta_min=lr / 4, last_epoch=-1)

@@ -50,23 +50,7 @@ def ortho_(model, strength=1e-4, blacklist=()):
             p.grad.add_(g.view_as(p), alpha=strength)
 
 
-class EMA:
-    """utils.apply_ema (utils/__init__.py:809-837) on whole state dicts with fused foreach ops."""
-
-    def __init__(self, source, target, decay=0.9999, start_itr=0):
-        self.decay, self.start_itr = decay, start_itr
-        sd, td = source.state_dict(), target.state_dict()
-        self.src = [sd[k] for k in sd]
-        self.dst = [td[k] for k in sd]
-        with torch.no_grad():
-            torch._foreach_copy_(self.dst, self.src)
-
-    def update(self, itr=None):
-        decay = 0.0 if (itr and itr < self.start_itr) else self.decay
-        with torch.no_grad():
-            fl = [(d, s) for d, s in zip(self.dst, self.src) if d.is_floating_point()]
-            torch._foreach_mul_([d for d, _ in fl], decay)
-            torch._foreach_add_([d for d, _ in fl], [s for _, s in fl], alpha=1 - decay)
+from .optim import FusedEMA as EMA  # noqa: E402  (utils.apply_ema as one multi-tensor launch)
 
 
 def check_config(config):
@@ -114,9 +98,7 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
             grad_hook(D)
         if config.get("D_ortho", 0.0) > 0.0:
             ortho_(d_params, config["D_ortho"])
-        if config.get("clip_norm") is not None:
-            torch.nn.utils.clip_grad_norm_(d_params, config["clip_norm"])
-        D.optim.step()
+        D.optim.step(clip_norm=config.get("clip_norm"))  # clip_grad_norm_ + Adam, fused (train_fns.py:136-139)
         # ---- G step (train_fns.py:142-192)
         toggle_grad(d_params, False)
         toggle_grad(g_params, True)
@@ -136,8 +118,7 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
         if config.get("G_ortho", 0.0) > 0.0:
             ortho_(g_params, config["G_ortho"], blacklist=g_black)
         if config.get("clip_norm") is not None:  # the reference only steps G inside this branch (train_fns.py:190-192)
-            torch.nn.utils.clip_grad_norm_(g_params, config["clip_norm"])
-            G.optim.step()
+            G.optim.step(clip_norm=config["clip_norm"])
         if ema is not None:
             ema.update(state["itr"])
         vals = torch.stack([g_loss.detach(), l_real.detach(), l_fake.detach(), unif_d.detach(), iea_l.detach()]).tolist()

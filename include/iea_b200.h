@@ -186,6 +186,33 @@ int iea_bn_finalize_bwd(const float* dscale, const float* dshift, const float* s
 int iea_affine_act(const void* x, int x_dtype, const float* scale, const float* shift, int64_t n,
                    int64_t hw, int c, int relu, void* y, int y_dtype, iea_stream_t stream);
 
+/* ---- optimizer step: clip + Adam + EMA as multi-tensor kernels ----- */
+/* One <= 65536-element slice of one tensor.  p: parameter (updated in place); g: its gradient;
+ * m, v: Adam's exp_avg / exp_avg_sq; ema: the moving-average copy of p (NULL: none).
+ * iea_mt_lerp reads p as the destination and g as the source. */
+typedef struct iea_mt_chunk {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float* ema;
+  int32_t n;
+  int32_t tensor;
+} iea_mt_chunk;
+/* partial[i] = sum of squares of chunk i's gradient (torch.nn.utils.clip_grad_norm_'s norm,
+ * train_fns.py:133-136,190-191; reduced in iea_mt_adam in a fixed order). */
+int iea_mt_sqnorm(const iea_mt_chunk* chunks, int n_chunks, float* partial, iea_stream_t stream);
+/* torch.optim.Adam step (model.py:410-416, 858-864: no weight decay, no amsgrad) on every chunk, with
+ * the gradient scaled by min(1, max_norm / (norm + 1e-6)) when partial != NULL and max_norm > 0, and
+ * ema = d*ema + (1-d)*p for chunks that carry one (utils/__init__.py:825-837).
+ * scalars (device, 5 floats, zero before the first step): [0] step count, incremented here;
+ * [1] clip coefficient; [2] 1-beta1^t; [3] sqrt(1-beta2^t); [4] gradient norm before clipping.
+ * hyper (device, 2 floats): [0] learning rate, [1] EMA decay d.  Two launches. */
+int iea_mt_adam(const iea_mt_chunk* chunks, int n_chunks, const float* partial, float max_norm, float beta1,
+                float beta2, float eps, float* scalars, const float* hyper, iea_stream_t stream);
+/* p = d*p + (1-d)*g per chunk (d = hyper[1]): the moving average of buffers (u0, sv0, running stats) */
+int iea_mt_lerp(const iea_mt_chunk* chunks, int n_chunks, const float* hyper, iea_stream_t stream);
+
 /* ---- layout / elementwise helpers ------------------------------------------------- */
 /* NCHW (src_dtype) <-> NHWC (dst_dtype) */
 int iea_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, int c,
