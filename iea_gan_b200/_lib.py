@@ -51,6 +51,11 @@ class MtChunk(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("n", i32), ("tensor", i32)]
 
 
+class OrthoItem(C.Structure):
+    _fields_ = [("w", vp), ("grad", vp), ("gram", vp), ("rownorm", vp), ("rows", i32), ("cols", i32), ("tall", i32),
+                ("strength", f32)]
+
+
 class AugDraws(C.Structure):
     _fields_ = [("brightness", vp), ("contrast", vp), ("tx", vp), ("ty", vp), ("ox", vp), ("oy", vp),
                 ("cut_h", i32), ("cut_w", i32)]
@@ -114,6 +119,7 @@ _SIG = {
     "iea_mt_sqnorm": [vp, i32, vp, vp],
     "iea_mt_adam": [vp, i32, vp, f32, f32, f32, f32, vp, vp, vp],
     "iea_mt_lerp": [vp, i32, vp, vp],
+    "iea_ortho_grouped": [vp, vp, i32, vp, i32, vp, i32, vp],
 }
 
 _lib = None

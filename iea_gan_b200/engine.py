@@ -51,6 +51,7 @@ def conv_impl():
 LAUNCHES = [0]  # kernels launched through the C ABI (bench.py reports it)
 
 
+GRAPH_KEEP = None  # while a CUDA graph is being captured: list that keeps pinned host tables alive for its replays
 TRACE = None    # debugging aid: a list that receives (shape tag, output tensor) of every conv() call
 PROFILE = None  # tools/prof_layers.py sets this to a list: (name, tag, start event, end event) per C-ABI call
 
@@ -168,6 +169,8 @@ class Tape:
         host = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).pin_memory()
         table = host.to(dev, non_blocking=True)
         K("iea_sn_weight_bwd_grouped", ptr(table), len(jobs), b0, ptr(_f32(b0, dev)), L.stream(), launches=2)
+        if GRAPH_KEEP is not None:
+            GRAPH_KEEP.append(host)  # the captured host->device copy re-reads this buffer at every replay
         self._sn_keep = (host, table)  # (stream-ordered allocators make dropping the job tensors safe once enqueued)
 
     def galloc(self, param, accumulate_ok=False):

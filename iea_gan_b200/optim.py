@@ -17,7 +17,8 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from ._lib import call, ptr
+from ._lib import ptr
+from .engine import K as call  # (counts the launches for bench.py's gpu_launches and honours the per-call profiler)
 
 CHUNK = 65536  # elements per multi-tensor work item (one 256-thread block each)
 
@@ -119,7 +120,7 @@ class FusedAdam(torch.optim.Optimizer):
             dev = L.require_device(ps[0])
             with torch.cuda.device(dev):
                 st = self._group_state(gi, group, ps)
-                if st["lr"] != group["lr"]:
+                if st["lr"] != group["lr"] and not torch.cuda.is_current_stream_capturing():
                     st["hyper"][0:1].fill_(group["lr"])
                     st["lr"] = group["lr"]
                 s = L.stream()
@@ -129,8 +130,16 @@ class FusedAdam(torch.optim.Optimizer):
                     part = st["partial"]
                 b1, b2 = group["betas"]
                 call("iea_mt_adam", ptr(st["table"]), st["n"], ptr(part), float(clip_norm or 0.0), b1, b2,
-                     group["eps"], ptr(st["scalars"]), ptr(st["hyper"]), s)
+                     group["eps"], ptr(st["scalars"]), ptr(st["hyper"]), s, launches=2)
         return loss
+
+    def refresh_hyper(self):
+        """Push a changed learning rate to the device scalar the (possibly graph-captured) kernels read."""
+        for gi, group in enumerate(self.param_groups):
+            st = self._cache.get(gi)
+            if st is not None and st["lr"] != group["lr"]:
+                st["hyper"][0:1].fill_(group["lr"])
+                st["lr"] = group["lr"]
 
     def grad_norm(self, gi=0):
         """Total gradient norm measured by the last step(clip_norm=...) (a device scalar; no sync)."""
@@ -168,11 +177,88 @@ class FusedEMA:
         return self._st
 
     @torch.no_grad()
-    def update(self, itr=None):
+    def refresh_hyper(self, itr=None):
+        """Decay switch at start_itr, pushed to the device scalar the kernel reads."""
         st = self._state()
         decay = 0.0 if (itr and itr < self.start_itr) else self.decay
-        with torch.cuda.device(st["device"]):
-            if st["decay"] != decay:
+        if st["decay"] != decay:
+            with torch.cuda.device(st["device"]):
                 st["hyper"][1:2].fill_(decay)
-                st["decay"] = decay
+            st["decay"] = decay
+        return st
+
+    @torch.no_grad()
+    def update(self, itr=None):
+        capturing = torch.cuda.is_current_stream_capturing()
+        st = self._state() if capturing else self.refresh_hyper(itr)  # (a captured fill would pin the decay)
+        with torch.cuda.device(st["device"]):
             call("iea_mt_lerp", ptr(st["table"]), st["n"], ptr(st["hyper"]), L.stream())
+
+
+class OrthoReg:
+    """utils.ortho (utils/__init__.py:843-859) for a fixed parameter list as three grouped launches
+    (csrc/ortho.cu).  Parameters with fewer than 2 axes and blacklisted ones (G.shared, train_fns.py:187) are
+    skipped, as in the reference."""
+
+    TALL = 2048  # rows above which W (W^T W) - diag(|w|^2) W replaces the rows x rows Gram matrix
+
+    def __init__(self, params, strength=1e-4, blacklist=()):
+        self.params = [p for p in params if p.dim() >= 2 and not any(p is b for b in blacklist)]
+        self.strength = strength
+        self._st = None
+
+    def _state(self):
+        ps = [p for p in self.params if p.grad is not None]
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        if self._st is not None and self._st["key"] == key:
+            return self._st
+        dev = ps[0].device
+        L.require_device(ps[0])
+        items = (L.OrthoItem * len(ps))()
+        geo, gsz, rsz = [], 0, 0
+        for p in ps:
+            rows, cols = p.shape[0], p.numel() // p.shape[0]
+            tall = rows > cols and rows > self.TALL
+            d = cols if tall else rows
+            geo.append((rows, cols, tall, d, gsz, rsz))
+            gsz += d * d
+            rsz += rows if tall else 0
+        gram = torch.empty(max(gsz, 1), dtype=torch.float32, device=dev)
+        rn = torch.empty(max(rsz, 1), dtype=torch.float32, device=dev)
+        rn_rows, gt, at = [], [], []
+        for i, (p, (rows, cols, tall, d, go, ro)) in enumerate(zip(ps, geo)):
+            it = items[i]
+            it.w, it.grad, it.gram = p.data_ptr(), p.grad.data_ptr(), gram.data_ptr() + 4 * go
+            it.rownorm = rn.data_ptr() + 4 * ro if tall else None
+            it.rows, it.cols, it.tall, it.strength = rows, cols, int(tall), self.strength
+            if tall:
+                rn_rows += [(i, r) for r in range(rows)]
+            td = (d + 63) // 64
+            gt += [(i, a, b, 0) for a in range(td) for b in range(td)]
+            at += [(i, a, b, 0) for a in range((rows + 63) // 64) for b in range((cols + 63) // 64)]
+        dev_i32 = lambda rows_: torch.tensor(np.array(rows_, dtype=np.int32).reshape(-1), dtype=torch.int32, device=dev)
+        self._st = {"key": key, "items": torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(dev),
+                    "rn_rows": dev_i32(rn_rows) if rn_rows else None, "n_rn": len(rn_rows), "gt": dev_i32(gt),
+                    "n_gt": len(gt), "at": dev_i32(at), "n_at": len(at), "gram": gram, "rn": rn, "device": dev}
+        return self._st
+
+    @torch.no_grad()
+    def apply(self):
+        if not any(p.grad is not None for p in self.params):
+            return
+        st = self._state()
+        with torch.cuda.device(st["device"]):
+            call("iea_ortho_grouped", ptr(st["items"]), ptr(st["rn_rows"]), st["n_rn"], ptr(st["gt"]), st["n_gt"],
+                 ptr(st["at"]), st["n_at"], L.stream(), launches=3 if st["n_rn"] else 2)
+
+
+def ortho(model, strength=1e-4, blacklist=None):
+    """Drop-in for utils.ortho(model, strength, blacklist) (utils/__init__.py:843-859; `utils.ortho =
+    iea_gan_b200.optim.ortho` is the one-line hook-up): same gradient update, grouped kernels."""
+    plans = model.__dict__.setdefault("_iea_ortho", {})
+    bl = tuple(blacklist or ())
+    key = (float(strength), tuple(id(b) for b in bl))
+    plan = plans.get(key)
+    if plan is None:
+        plan = plans[key] = OrthoReg(model.parameters(), strength, bl)
+    plan.apply()

@@ -32,24 +32,7 @@ class NormalNoise:
         return self.t
 
 
-def ortho_(model, strength=1e-4, blacklist=()):
-    """Modified orthogonal regularisation added straight to .grad (utils/__init__.py:843-859):
-    grad += strength * 2 (W W^T * (1 - I)) W, evaluated as 2 (W (W^T W) - diag(|w_i|^2) W) so the
-    rows x rows Gram matrix (24576^2 for G.linear at H_base 3) is never formed."""
-    with torch.no_grad():
-        for p in (model if isinstance(model, (list, tuple)) else model.parameters()):
-            if p.dim() < 2 or any(p is b for b in blacklist) or p.grad is None:
-                continue
-            w = p.view(p.shape[0], -1)
-            if w.shape[0] <= w.shape[1]:
-                gram = w @ w.t()
-                gram.fill_diagonal_(0.0)
-                g = 2 * (gram @ w)
-            else:
-                g = 2 * (w @ (w.t() @ w) - (w * w).sum(1, keepdim=True) * w)
-            p.grad.add_(g.view_as(p), alpha=strength)
-
-
+from .optim import OrthoReg, ortho as ortho_  # noqa: E402,F401  (utils.ortho as grouped kernels)
 from .optim import FusedEMA as EMA  # noqa: E402  (utils.apply_ema as one multi-tensor launch)
 
 
@@ -66,9 +49,20 @@ def check_config(config):
                                   "the drop-in modules for other settings" % (want, bad))
 
 
-def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
+GRAPH_SUPPORTED = True  # make_train_step(cuda_graph=True): bench.py probes this
+
+
+def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, cuda_graph=False, graph_warmup=3):
     """Returns train(x, y) -> dict of the five floats train_fns.train returns.
-    grad_hook(net) is called after each backward (the data-parallel all-reduce point)."""
+    grad_hook(net) is called after each backward (explicit data-parallel all-reduce point; nets prepared with
+    dp.attach() need none).
+
+    cuda_graph=True: after `graph_warmup` eager steps (which size the caches and the allocator) the WHOLE step --
+    both forwards and backwards, the losses, clip + Adam, EMA, and under dp.attach() the NCCL all-reduces -- is
+    captured once into a CUDA graph and replayed: ~2000 kernel launches become one graph launch, which removes the
+    host launch floor (81 ms at one event per step).  Shapes must then stay fixed; the random draws come from the
+    CUDA generator as before (its Philox offset advances per replay); learning-rate / EMA-decay changes are picked
+    up from device memory without re-capture."""
     check_config(config)
     contra = losses.Conditional_Contrastive_loss(None, config["batch_size"], config["pos_collected_numerator"])
     use_unif = bool(config.get("Uniformity_loss", True))
@@ -76,8 +70,12 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
     state = state if state is not None else {"itr": 0}
     g_params, d_params = list(G.parameters()), list(D.parameters())  # walked once, not ten times per step
     g_black = list(G.shared.parameters())
+    d_ortho = OrthoReg(d_params, config["D_ortho"]) if config.get("D_ortho", 0.0) > 0.0 else None
+    g_ortho = OrthoReg(g_params, config["G_ortho"], g_black) if config.get("G_ortho", 0.0) > 0.0 else None
+    names = ("G_loss", "D_loss_real", "D_loss_fake", "unif_loss_d", "iea_loss")
 
-    def train(x, y):
+    def body(x, y):
+        """One step; returns the (5,) device tensor of reported losses (no host synchronisation inside)."""
         G.optim.zero_grad()
         D.optim.zero_grad()
         toggle_grad(d_params, True)
@@ -96,8 +94,8 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
         d_loss.backward()
         if grad_hook is not None:
             grad_hook(D)
-        if config.get("D_ortho", 0.0) > 0.0:
-            ortho_(d_params, config["D_ortho"])
+        if d_ortho is not None:  # utils.ortho(D, D_ortho), train_fns.py:133-134
+            d_ortho.apply()
         D.optim.step(clip_norm=config.get("clip_norm"))  # clip_grad_norm_ + Adam, fused (train_fns.py:136-139)
         # ---- G step (train_fns.py:142-192)
         toggle_grad(d_params, False)
@@ -115,12 +113,46 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None):
         g_loss.backward()
         if grad_hook is not None:
             grad_hook(G)
-        if config.get("G_ortho", 0.0) > 0.0:
-            ortho_(g_params, config["G_ortho"], blacklist=g_black)
+        if g_ortho is not None:  # utils.ortho(G, G_ortho, blacklist=G.shared), train_fns.py:185-188
+            g_ortho.apply()
         if config.get("clip_norm") is not None:  # the reference only steps G inside this branch (train_fns.py:190-192)
             G.optim.step(clip_norm=config["clip_norm"])
         if ema is not None:
             ema.update(state["itr"])
-        vals = torch.stack([g_loss.detach(), l_real.detach(), l_fake.detach(), unif_d.detach(), iea_l.detach()]).tolist()
-        return dict(zip(("G_loss", "D_loss_real", "D_loss_fake", "unif_loss_d", "iea_loss"), vals))
+        return torch.stack([g_loss.detach(), l_real.detach(), l_fake.detach(), unif_d.detach(), iea_l.detach()])
+
+    if not cuda_graph:
+        def train(x, y):
+            return dict(zip(names, body(x, y).tolist()))
+        return train
+
+    gs = {"calls": 0, "graph": None}
+
+    def train(x, y):
+        if gs["graph"] is None:
+            gs["calls"] += 1
+            if gs["calls"] <= graph_warmup:
+                return dict(zip(names, body(x, y).tolist()))
+            # capture (the capture itself executes nothing: the replay below performs this call's step)
+            from . import engine
+            gs["x"], gs["y"] = x.detach().clone(), y.detach().clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            engine.GRAPH_KEEP = keep = []  # pinned host tables referenced by captured copies stay alive with the graph
+            try:
+                with torch.cuda.graph(g):
+                    gs["vals"] = body(gs["x"], gs["y"])
+            finally:
+                engine.GRAPH_KEEP = None
+            gs["graph"], gs["keep"] = g, keep
+        else:
+            gs["x"].copy_(x, non_blocking=True)
+            gs["y"].copy_(y, non_blocking=True)
+        # everything host-dependent that the captured kernels read from device memory
+        for o in (G.optim, D.optim):
+            o.refresh_hyper()
+        if ema is not None:
+            ema.refresh_hyper(state["itr"])
+        gs["graph"].replay()
+        return dict(zip(names, gs["vals"].tolist()))
     return train

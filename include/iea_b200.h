@@ -213,6 +213,25 @@ int iea_mt_adam(const iea_mt_chunk* chunks, int n_chunks, const float* partial, 
 /* p = d*p + (1-d)*g per chunk (d = hyper[1]): the moving average of buffers (u0, sv0, running stats) */
 int iea_mt_lerp(const iea_mt_chunk* chunks, int n_chunks, const float* hyper, iea_stream_t stream);
 
+/* ---- modified orthogonal regularisation ------------------------------ */
+/* One >= 2-D parameter viewed as W (rows x cols), row-major fp32.  gram: scratch of d*d floats with
+ * d = tall ? cols : rows; rownorm: rows floats (tall only).  utils.ortho (utils/__init__.py:843-859):
+ * grad += strength * 2 * ((W W^T) o (1 - I)) W; tall = evaluate it as W (W^T W) - diag(|w_i|^2) W. */
+typedef struct iea_ortho_item {
+  const float* w;
+  float* grad;
+  float* gram;
+  float* rownorm;
+  int32_t rows, cols;
+  int32_t tall;
+  float strength;
+} iea_ortho_item;
+/* rownorm_rows: (item, row) pairs of the tall items; gram_tiles / apply_tiles: (item, tile row, tile col, 0)
+ * with 64 x 64 tiles of the Gram matrix / of the parameter.  Three launches for the whole net. */
+int iea_ortho_grouped(const iea_ortho_item* items, const int32_t* rownorm_rows, int n_rownorm_rows,
+                      const int32_t* gram_tiles, int n_gram_tiles, const int32_t* apply_tiles,
+                      int n_apply_tiles, iea_stream_t stream);
+
 /* ---- layout / elementwise helpers ------------------------------------------------- */
 /* NCHW (src_dtype) <-> NHWC (dst_dtype) */
 int iea_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, int c,

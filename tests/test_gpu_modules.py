@@ -58,11 +58,15 @@ def check(m, rec, adt, feature_only=False, n_out=1):
         if r is not None:
             assert rel(t.grad, r) < t_g, ("input grad", rel(t.grad, r))
     ps = dict(m.named_parameters())
+    scale = max(float(r.norm()) for r in rec["param_grads"].values())
     for k, r in rec["param_grads"].items():
         assert ps[k].grad is not None, k
-        # exactly-zero reference gradients (conv biases in front of a batch-norm) are rounding noise here
-        assert rel(ps[k].grad, r) < t_g or float(ps[k].grad.abs().max()) < (1e-5 if adt == "fp32" else 5e-3), \
-            (k, rel(ps[k].grad, r))
+        if float(r.norm()) < 1e-6 * scale:
+            # exactly-zero gradient (a conv bias in front of a batch-norm; the reference's value is rounding noise
+            # too): ours must be noise on the scale of the module's gradients
+            assert float(ps[k].grad.norm()) < (1e-6 if adt == "fp32" else 1e-3) * scale, (k, float(ps[k].grad.norm()), scale)
+            continue
+        assert rel(ps[k].grad, r) < t_g, (k, rel(ps[k].grad, r))
     bufs = dict(m.named_buffers())
     for k, r in rec["after"].items():
         assert rel(bufs[k].float(), r.float()) < (1e-4 if (adt == "fp32" or feature_only) else 3e-2), (k, rel(bufs[k], r))
