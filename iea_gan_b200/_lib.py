@@ -107,13 +107,14 @@ _SIG = {
     "iea_loss_hinge_dis_bwd": [vp, vp, vp, i64, vp, vp, vp],
     "iea_loss_mean": [vp, i64, f32, vp, vp],
     "iea_loss_mean_bwd": [vp, i64, f32, vp, vp],
+    "iea_loss_scratch_floats": [i32, i32, i32],
     "iea_loss_l2": [vp, vp, i64, vp, vp],
     "iea_loss_l2_bwd": [vp, vp, vp, i64, vp, vp, vp],
-    "iea_loss_contrastive_fwd": [vp, vp, i32, i32, i32, f32, f32, vp, vp, vp],
+    "iea_loss_contrastive_fwd": [vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp],
     "iea_loss_contrastive_bwd": [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp],
-    "iea_loss_iea_fwd": [vp, vp, i32, i32, i32, vp, vp, vp],
+    "iea_loss_iea_fwd": [vp, vp, i32, i32, i32, vp, vp, vp, vp],
     "iea_loss_iea_bwd": [vp, vp, vp, i32, i32, i32, vp, vp],
-    "iea_loss_unif_fwd": [vp, i32, i32, i32, f32, vp, vp, vp],
+    "iea_loss_unif_fwd": [vp, i32, i32, i32, f32, vp, vp, vp, vp],
     "iea_loss_unif_bwd": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
     "iea_adu_postprocess": [vp, i64, i32, i32, vp, vp],
     "iea_mt_sqnorm": [vp, i32, vp, vp],
@@ -122,6 +123,7 @@ _SIG = {
     "iea_ortho_grouped": [vp, vp, i32, vp, i32, vp, i32, vp],
 }
 
+_RET64 = {"iea_loss_scratch_floats"}  # sizes come back as int64_t; everything else is an int status
 _lib = None
 _checked_devices = set()
 
@@ -146,7 +148,7 @@ def lib():
         L.iea_last_error.argtypes = []
         for name, sig in _SIG.items():
             fn = getattr(L, name)  # raises AttributeError if the symbol is not exported
-            fn.restype = C.c_int
+            fn.restype = C.c_int64 if name in _RET64 else C.c_int
             fn.argtypes = sig
         _lib = L
     return _lib

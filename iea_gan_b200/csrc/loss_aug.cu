@@ -140,21 +140,65 @@ __global__ void sum_events_kernel(const float* ev, int events, int stride, float
   }
 }
 
-// dot products of all row pairs of an event: out[i*seq+j] = A_i . B_j   (8 warps)
-__device__ void gram(const float* A, const float* B, int seq, int dim, float* out) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int p = wid; p < seq * seq; p += nw) {
-    int i = p / seq, j = p - i * seq;
+// Gram matrices of an event, spread over the chip: grid (events, ceil(dim / GSL)) CTAs each take a GSL-column
+// slice of the (seq x dim) operands into shared memory and write the partial seq x seq products
+//   part[e][s][0 .. seq*seq)        = A_e[:, slice] . B_e[:, slice]^T
+//   part[e][s][seq*seq + 2i, +2i+1] = (a_i . c_i, c_i . c_i) over the slice        (when Cm != NULL)
+// the per-event loss kernels then add the slices in a fixed order (deterministic).  One CTA per event computing
+// the whole 40 x 40 x 1024 Gram with a warp per pair (round 1) took 2.7 ms for 8 events: pure load latency.
+constexpr int GSL = 128;
+__global__ void __launch_bounds__(256) gram_partial_kernel(const float* A, const float* B, const float* Cm, int seq,
+                                                           int dim, float* part, int stride) {
+  extern __shared__ float sm[];
+  const int e = blockIdx.x, sl = blockIdx.y, k0 = sl * GSL;
+  const int kw = dim - k0 < GSL ? dim - k0 : GSL;
+  float* As = sm;
+  float* Bs = (B == A) ? As : As + seq * (GSL + 1);
+  const float* Ae = A + (int64_t)e * seq * dim;
+  const float* Be = B + (int64_t)e * seq * dim;
+  for (int idx = threadIdx.x; idx < seq * GSL; idx += 256) {
+    const int i = idx / GSL, k = idx - i * GSL;
+    As[i * (GSL + 1) + k] = k < kw ? Ae[(int64_t)i * dim + k0 + k] : 0.f;
+    if (B != A) Bs[i * (GSL + 1) + k] = k < kw ? Be[(int64_t)i * dim + k0 + k] : 0.f;
+  }
+  __syncthreads();
+  float* out = part + ((int64_t)e * gridDim.y + sl) * stride;
+  for (int p = threadIdx.x; p < seq * seq; p += 256) {
+    const int i = p / seq, j = p - i * seq;
+    const float* a = As + i * (GSL + 1);
+    const float* b = Bs + j * (GSL + 1);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < GSL; k += 2) { s0 = fmaf(a[k], b[k], s0); s1 = fmaf(a[k + 1], b[k + 1], s1); }
+    out[p] = s0 + s1;
+  }
+  if (Cm) {
+    const float* Ce = Cm + (int64_t)e * seq * dim;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = wid; i < seq; i += 8) {
+      float ac = 0.f, cc = 0.f;
+      for (int k = lane; k < kw; k += 32) {
+        const float c = Ce[(int64_t)i * dim + k0 + k];
+        ac = fmaf(As[i * (GSL + 1) + k], c, ac);
+        cc = fmaf(c, c, cc);
+      }
+      ac = warp_sum(ac); cc = warp_sum(cc);
+      if (lane == 0) { out[seq * seq + 2 * i] = ac; out[seq * seq + 2 * i + 1] = cc; }
+    }
+  }
+}
+// sum of the slices of one event's partial Gram (and row dots) into shared memory
+__device__ __forceinline__ void gram_collect(const float* part, int e, int nsl, int stride, int count, float* dst) {
+  for (int p = threadIdx.x; p < count; p += blockDim.x) {
     float s = 0.f;
-    for (int k = lane; k < dim; k += 32) s = fmaf(A[(int64_t)i * dim + k], B[(int64_t)j * dim + k], s);
-    s = warp_sum(s);
-    if (lane == 0) out[p] = s;
+    for (int sl = 0; sl < nsl; ++sl) s += part[((int64_t)e * nsl + sl) * stride + p];
+    dst[p] = s;
   }
 }
 
 // saved per event: P[seq][seq] (weights exp(.)/den_i, 0 on the diagonal), Cs[seq][seq] (cosines),
 // q[seq] (num/den), cp[seq] (cos(e_i,p_i)), ne[seq], np[seq], then the event's loss  -> 2*seq*seq+4*seq+1
-__global__ void __launch_bounds__(256) contrastive_fwd_kernel(const float* embed, const float* proxy, int seq, int dim,
+__global__ void __launch_bounds__(256) contrastive_fwd_kernel(const float* part, int nsl, int stride, int seq, int dim,
                                                               float temp, float margin, float* saved_all) {
   extern __shared__ float sm[];
   float* S = sm;               // [seq][seq]
@@ -164,20 +208,15 @@ __global__ void __launch_bounds__(256) contrastive_fwd_kernel(const float* embed
   float* li = cp + seq;        // per-row loss
   __shared__ float red[33];
   const int e = blockIdx.x;
-  const float* E = embed + (int64_t)e * seq * dim;
-  const float* Pr = proxy + (int64_t)e * seq * dim;
   float* saved = saved_all + (int64_t)e * (2 * seq * seq + 4 * seq + 1);
-  gram(E, E, seq, dim, S);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = wid; i < seq; i += 8) {
-    float a = 0.f, b = 0.f;
-    for (int k = lane; k < dim; k += 32) {
-      float p = Pr[(int64_t)i * dim + k];
-      a = fmaf(p, p, a);
-      b = fmaf(p, E[(int64_t)i * dim + k], b);
+  gram_collect(part, e, nsl, stride, seq * seq, S);  // E E^T
+  for (int i = threadIdx.x; i < seq; i += blockDim.x) {  // e_i . p_i and |p_i|^2
+    float ac = 0.f, cc = 0.f;
+    for (int sl = 0; sl < nsl; ++sl) {
+      const float* o = part + ((int64_t)e * nsl + sl) * stride + seq * seq + 2 * i;
+      ac += o[0]; cc += o[1];
     }
-    a = warp_sum(a); b = warp_sum(b);
-    if (lane == 0) { np_[i] = sqrtf(a); cp[i] = b; }
+    cp[i] = ac; np_[i] = sqrtf(cc);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < seq; i += blockDim.x) ne[i] = sqrtf(S[i * seq + i]);
@@ -258,15 +297,15 @@ __global__ void __launch_bounds__(256) contrastive_bwd_kernel(const float* embed
 }
 
 // saved per event: D[seq][seq] = (softmax(F F^T) - softmax(R R^T)) / seq, then the event's loss
-__global__ void __launch_bounds__(256) iea_fwd_kernel(const float* kf, const float* kr, int seq, int dim,
-                                                      float* saved_all) {
+__global__ void __launch_bounds__(256) iea_fwd_kernel(const float* part_f, const float* part_r, int nsl, int stride,
+                                                      int seq, int dim, float* saved_all) {
   extern __shared__ float sm[];
   float* SF = sm; float* SR = SF + seq * seq; float* li = SR + seq * seq;
   __shared__ float red[33];
   const int e = blockIdx.x;
   float* saved = saved_all + (int64_t)e * (seq * seq + 1);
-  gram(kf + (int64_t)e * seq * dim, kf + (int64_t)e * seq * dim, seq, dim, SF);
-  gram(kr + (int64_t)e * seq * dim, kr + (int64_t)e * seq * dim, seq, dim, SR);
+  gram_collect(part_f, e, nsl, stride, seq * seq, SF);
+  gram_collect(part_r, e, nsl, stride, seq * seq, SR);
   __syncthreads();
   for (int i = threadIdx.x; i < seq; i += blockDim.x) {
     float mf = -3e38f, mr = -3e38f;
@@ -301,28 +340,30 @@ __global__ void __launch_bounds__(256) iea_bwd_kernel(const float* kf, const flo
   }
   __syncthreads();
   const float* F = kf + (int64_t)e * seq * dim;
-  for (int idx = threadIdx.x; idx < seq * dim; idx += blockDim.x) {
-    int i = idx / dim, kk = idx - i * dim;
+  const int k0 = blockIdx.y * CBWD_SLICE;  // (the gradient is independent per feature column: slices over the chip)
+  const int ncol = dim - k0 < CBWD_SLICE ? dim - k0 : CBWD_SLICE;
+  for (int idx = threadIdx.x; idx < seq * ncol; idx += blockDim.x) {
+    const int i = idx / ncol, kk = k0 + idx - i * ncol;
     float g = 0.f;
     for (int j = 0; j < seq; ++j) g = fmaf(sm[i * seq + j], F[(int64_t)j * dim + kk], g);
-    dkf[(int64_t)e * seq * dim + idx] = g;
+    dkf[(int64_t)e * seq * dim + (int64_t)i * dim + kk] = g;
   }
 }
 
 // saved per event: Wm[seq][seq] = exp(-t |x_i - x_j|^2) (0 on the diagonal), S = sum_{i<j}, loss
-__global__ void __launch_bounds__(256) unif_fwd_kernel(const float* x, int seq, int dim, float t, float* saved_all) {
+__global__ void __launch_bounds__(256) unif_fwd_kernel(const float* part, int nsl, int stride, int seq, int dim,
+                                                       float t, float* saved_all) {
+  extern __shared__ float sm[];  // [seq][seq] Gram
   __shared__ float red[33];
   const int e = blockIdx.x;
-  const float* X = x + (int64_t)e * seq * dim;
   float* saved = saved_all + (int64_t)e * (seq * seq + 2);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int p = wid; p < seq * seq; p += 8) {
-    int i = p / seq, j = p - i * seq;
-    float s = 0.f;
-    if (i != j)
-      for (int k = lane; k < dim; k += 32) { float d = X[(int64_t)i * dim + k] - X[(int64_t)j * dim + k]; s = fmaf(d, d, s); }
-    s = warp_sum(s);
-    if (lane == 0) saved[p] = (i == j) ? 0.f : __expf(-t * s);
+  gram_collect(part, e, nsl, stride, seq * seq, sm);
+  __syncthreads();
+  // |x_i - x_j|^2 = |x_i|^2 + |x_j|^2 - 2 x_i . x_j   (torch.pdist(x)^2, loss.py:8-9)
+  for (int p = threadIdx.x; p < seq * seq; p += blockDim.x) {
+    const int i = p / seq, j = p - i * seq;
+    const float d2 = fmaxf(sm[i * seq + i] + sm[j * seq + j] - 2.f * sm[p], 0.f);
+    saved[p] = (i == j) ? 0.f : __expf(-t * d2);
   }
   __syncthreads();
   float a = 0.f;
@@ -339,12 +380,14 @@ __global__ void __launch_bounds__(256) unif_bwd_kernel(const float* x, const flo
   const float* Wm = saved_all + (int64_t)e * (seq * seq + 2);
   const float k = dloss[0] / events * (-2.f * t) / Wm[seq * seq];
   const float* X = x + (int64_t)e * seq * dim;
-  for (int idx = threadIdx.x; idx < seq * dim; idx += blockDim.x) {
-    int i = idx / dim, kk = idx - i * dim;
-    const float xi = X[idx];
+  const int k0 = blockIdx.y * CBWD_SLICE;
+  const int ncol = dim - k0 < CBWD_SLICE ? dim - k0 : CBWD_SLICE;
+  for (int idx = threadIdx.x; idx < seq * ncol; idx += blockDim.x) {
+    const int i = idx / ncol, kk = k0 + idx - i * ncol;
+    const float xi = X[(int64_t)i * dim + kk];
     float g = 0.f;
     for (int j = 0; j < seq; ++j) g = fmaf(Wm[i * seq + j], xi - X[(int64_t)j * dim + kk], g);
-    dx[(int64_t)e * seq * dim + idx] = k * g;
+    dx[(int64_t)e * seq * dim + (int64_t)i * dim + kk] = k * g;
   }
 }
 }  // namespace
@@ -390,10 +433,23 @@ int iea_loss_l2_bwd(const float* a, const float* b, const float* dout, int64_t n
   l2_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)st>>>(a, b, dout, n, da, db);
   return check_launch("iea_loss_l2_bwd");
 }
+int64_t iea_loss_scratch_floats(int events, int seq, int dim) {
+  return (int64_t)events * cdiv(dim, GSL) * 2 * ((int64_t)seq * seq + 2 * seq);
+}
+static int gram_partials(const float* A, const float* B, const float* Cm, int events, int seq, int dim, float* part,
+                         cudaStream_t st) {
+  const int stride = seq * seq + 2 * seq;
+  const size_t smem = (size_t)(B == A ? 1 : 2) * seq * (GSL + 1) * sizeof(float);
+  IEA_CHECK_ARG(smem <= 48 * 1024, "loss kernels: %d rows per event exceed the shared-memory Gram tile", seq);
+  gram_partial_kernel<<<dim3(events, cdiv(dim, GSL)), 256, smem, st>>>(A, B, Cm, seq, dim, part, stride);
+  return 0;
+}
 int iea_loss_contrastive_fwd(const float* embed, const float* proxy, int events, int seq, int dim, float temperature,
-                             float margin, float* loss, float* saved, iea_stream_t st) {
+                             float margin, float* loss, float* saved, float* scratch, iea_stream_t st) {
+  if (int rc = gram_partials(embed, embed, proxy, events, seq, dim, scratch, (cudaStream_t)st)) return rc;
   size_t smem = (size_t)(seq * seq + 4 * seq) * sizeof(float);
-  contrastive_fwd_kernel<<<events, 256, smem, (cudaStream_t)st>>>(embed, proxy, seq, dim, temperature, margin, saved);
+  contrastive_fwd_kernel<<<events, 256, smem, (cudaStream_t)st>>>(scratch, cdiv(dim, GSL), seq * seq + 2 * seq, seq, dim,
+                                                                  temperature, margin, saved);
   int stride = 2 * seq * seq + 4 * seq + 1;
   sum_events_kernel<<<1, 32, 0, (cudaStream_t)st>>>(saved + stride - 1, events, stride, loss);
   return check_launch("iea_loss_contrastive_fwd");
@@ -407,29 +463,35 @@ int iea_loss_contrastive_bwd(const float* embed, const float* proxy, const float
   return check_launch("iea_loss_contrastive_bwd");
 }
 int iea_loss_iea_fwd(const float* kf, const float* kr, int events, int seq, int dim, float* loss, float* saved,
-                     iea_stream_t st) {
+                     float* scratch, iea_stream_t st) {
+  const int stride = seq * seq + 2 * seq, nsl = cdiv(dim, GSL);
+  float* part_r = scratch + (int64_t)events * nsl * stride;
+  if (int rc = gram_partials(kf, kf, nullptr, events, seq, dim, scratch, (cudaStream_t)st)) return rc;
+  if (int rc = gram_partials(kr, kr, nullptr, events, seq, dim, part_r, (cudaStream_t)st)) return rc;
   size_t smem = (size_t)(2 * seq * seq + seq) * sizeof(float);
-  iea_fwd_kernel<<<events, 256, smem, (cudaStream_t)st>>>(kf, kr, seq, dim, saved);
-  int stride = seq * seq + 1;
-  sum_events_kernel<<<1, 32, 0, (cudaStream_t)st>>>(saved + stride - 1, events, stride, loss);
+  iea_fwd_kernel<<<events, 256, smem, (cudaStream_t)st>>>(scratch, part_r, nsl, stride, seq, dim, saved);
+  int sstride = seq * seq + 1;
+  sum_events_kernel<<<1, 32, 0, (cudaStream_t)st>>>(saved + sstride - 1, events, sstride, loss);
   return check_launch("iea_loss_iea_fwd");
 }
 int iea_loss_iea_bwd(const float* kf, const float* saved, const float* dloss, int events, int seq, int dim,
                      float* dkf, iea_stream_t st) {
-  iea_bwd_kernel<<<events, 256, (size_t)seq * seq * sizeof(float), (cudaStream_t)st>>>(kf, saved, dloss, events, seq,
-                                                                                       dim, dkf);
+  iea_bwd_kernel<<<dim3(events, cdiv(dim, CBWD_SLICE)), 256, (size_t)seq * seq * sizeof(float), (cudaStream_t)st>>>(
+      kf, saved, dloss, events, seq, dim, dkf);
   return check_launch("iea_loss_iea_bwd");
 }
 int iea_loss_unif_fwd(const float* x, int events, int seq, int dim, float t, float* loss, float* saved,
-                      iea_stream_t st) {
-  unif_fwd_kernel<<<events, 256, 0, (cudaStream_t)st>>>(x, seq, dim, t, saved);
+                      float* scratch, iea_stream_t st) {
+  if (int rc = gram_partials(x, x, nullptr, events, seq, dim, scratch, (cudaStream_t)st)) return rc;
+  unif_fwd_kernel<<<events, 256, (size_t)seq * seq * sizeof(float), (cudaStream_t)st>>>(
+      scratch, cdiv(dim, GSL), seq * seq + 2 * seq, seq, dim, t, saved);
   int stride = seq * seq + 2;
   sum_events_kernel<<<1, 32, 0, (cudaStream_t)st>>>(saved + stride - 1, events, stride, loss);
   return check_launch("iea_loss_unif_fwd");
 }
 int iea_loss_unif_bwd(const float* x, const float* saved, const float* dloss, int events, int seq, int dim, float t,
                       float* dx, iea_stream_t st) {
-  unif_bwd_kernel<<<events, 256, 0, (cudaStream_t)st>>>(x, saved, dloss, events, seq, dim, t, dx);
+  unif_bwd_kernel<<<dim3(events, cdiv(dim, CBWD_SLICE)), 256, 0, (cudaStream_t)st>>>(x, saved, dloss, events, seq, dim, t, dx);
   return check_launch("iea_loss_unif_bwd");
 }
 }

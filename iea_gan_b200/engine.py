@@ -1270,6 +1270,18 @@ class _LossFn(torch.autograd.Function):
         return (None, None) + tuple(grads)
 
 
+def _loss_scratch(events, dim, device):
+    """Partial-Gram scratch of the Gram-based losses (iea_loss_scratch_floats in include/iea_b200.h)."""
+    key = (events, dim)
+    n = _LOSS_SCRATCH.get(key)
+    if n is None:
+        n = _LOSS_SCRATCH[key] = call("iea_loss_scratch_floats", events, IMGS, dim)
+    return _f32(n, device)
+
+
+_LOSS_SCRATCH = {}
+
+
 def _events(x):
     n = x.shape[0]
     if n % IMGS:
@@ -1351,7 +1363,7 @@ def loss_contrastive(embed, proxy, temperature, margin):
         out = _scalar(e.device)
         saved = _f32(ev * (2 * IMGS * IMGS + 4 * IMGS + 1), e.device)
         K("iea_loss_contrastive_fwd", ptr(e), ptr(p), ev, IMGS, dim, temperature, margin, ptr(out), ptr(saved),
-          L.stream(), launches=2)
+          ptr(_loss_scratch(ev, dim, e.device)), L.stream(), launches=3)
         return out, saved
 
     def bwd(saved, xs, g, need):
@@ -1371,7 +1383,8 @@ def loss_iea(k_f, k_r):
     def fwd(f, r):
         out = _scalar(f.device)
         saved = _f32(ev * (IMGS * IMGS + 1), f.device)
-        K("iea_loss_iea_fwd", ptr(f), ptr(r), ev, IMGS, dim, ptr(out), ptr(saved), L.stream(), launches=2)
+        K("iea_loss_iea_fwd", ptr(f), ptr(r), ev, IMGS, dim, ptr(out), ptr(saved),
+          ptr(_loss_scratch(ev, dim, f.device)), L.stream(), launches=4)
         return out, saved
 
     def bwd(saved, xs, g, need):
@@ -1390,7 +1403,8 @@ def loss_uniformity(x, t):
     def fwd(x):
         out = _scalar(x.device)
         saved = _f32(ev * (IMGS * IMGS + 2), x.device)
-        K("iea_loss_unif_fwd", ptr(x), ev, IMGS, dim, t, ptr(out), ptr(saved), L.stream(), launches=2)
+        K("iea_loss_unif_fwd", ptr(x), ev, IMGS, dim, t, ptr(out), ptr(saved),
+          ptr(_loss_scratch(ev, dim, x.device)), L.stream(), launches=3)
         return out, saved
 
     def bwd(saved, xs, g, need):

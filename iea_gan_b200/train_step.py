@@ -132,7 +132,15 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
         if gs["graph"] is None:
             gs["calls"] += 1
             if gs["calls"] <= graph_warmup:
-                return dict(zip(names, body(x, y).tolist()))
+                # warm-up on a SIDE stream (torch's CUDA-graph recipe): autograd binds each parameter's gradient
+                # accumulator to the stream of its first backward, and a capture cannot depend on the legacy
+                # default stream.  Nets whose first backward already ran on the default stream cannot be captured.
+                side = gs.setdefault("side", torch.cuda.Stream())
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    vals = body(x, y)
+                torch.cuda.current_stream().wait_stream(side)
+                return dict(zip(names, vals.tolist()))
             # capture (the capture itself executes nothing: the replay below performs this call's step)
             from . import engine
             gs["x"], gs["y"] = x.detach().clone(), y.detach().clone()
@@ -140,7 +148,9 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
             g = torch.cuda.CUDAGraph()
             engine.GRAPH_KEEP = keep = []  # pinned host tables referenced by captured copies stay alive with the graph
             try:
-                with torch.cuda.graph(g):
+                # relaxed: the backward passes stage their job tables through pinned host buffers, and a pinned
+                # allocation (cudaHostAlloc) is an 'unsafe' call under the default global capture mode
+                with torch.cuda.graph(g, capture_error_mode="relaxed"):
                     gs["vals"] = body(gs["x"], gs["y"])
             finally:
                 engine.GRAPH_KEEP = None

@@ -312,18 +312,21 @@ int iea_loss_mean_bwd(const float* dout, int64_t n, float scale, float* dx, iea_
 int iea_loss_l2(const float* a, const float* b, int64_t n, float* out, iea_stream_t stream);
 int iea_loss_l2_bwd(const float* a, const float* b, const float* dout, int64_t n, float* da, float* db,
                     iea_stream_t stream);
+/* The three Gram-based losses split the (seq x seq x dim) products of an event over ceil(dim/128) CTAs;
+ * `scratch` receives the partial Gram matrices: iea_loss_scratch_floats(events, seq, dim) floats. */
+int64_t iea_loss_scratch_floats(int events, int seq, int dim);
 int iea_loss_contrastive_fwd(const float* embed, const float* proxy, int events, int seq, int dim,
                              float temperature, float margin, float* loss, float* saved /* events*(2*seq*seq+4*seq+1) */,
-                             iea_stream_t stream);
+                             float* scratch, iea_stream_t stream);
 int iea_loss_contrastive_bwd(const float* embed, const float* proxy, const float* saved,
                              const float* dloss, int events, int seq, int dim, float temperature,
                              float* dembed, float* dproxy, iea_stream_t stream);
 int iea_loss_iea_fwd(const float* kf, const float* kr, int events, int seq, int dim, float* loss,
-                     float* saved /* events*(seq*seq+1) */, iea_stream_t stream);
+                     float* saved /* events*(seq*seq+1) */, float* scratch, iea_stream_t stream);
 int iea_loss_iea_bwd(const float* kf, const float* saved, const float* dloss, int events, int seq,
                      int dim, float* dkf, iea_stream_t stream);
 int iea_loss_unif_fwd(const float* x, int events, int seq, int dim, float t, float* loss,
-                      float* saved /* events*(seq*seq+2) */, iea_stream_t stream);
+                      float* saved /* events*(seq*seq+2) */, float* scratch, iea_stream_t stream);
 int iea_loss_unif_bwd(const float* x, const float* saved, const float* dloss, int events, int seq,
                       int dim, float t, float* dx, iea_stream_t stream);
 
