@@ -117,6 +117,7 @@ _SIG = {
     "iea_loss_unif_fwd": [vp, i32, i32, i32, f32, vp, vp, vp, vp],
     "iea_loss_unif_bwd": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
     "iea_adu_postprocess": [vp, i64, i32, i32, vp, vp],
+    "iea_event_preprocess": [vp, i64, i32, i32, i32, vp, f32, vp, vp],
     "iea_mt_sqnorm": [vp, i32, vp, vp],
     "iea_mt_adam": [vp, i32, vp, f32, f32, f32, f32, vp, vp, vp],
     "iea_mt_lerp": [vp, i32, vp, vp],

@@ -328,9 +328,34 @@ __global__ void adu_kernel(const float* img, int64_t n, int h, int w, float* out
     out[i] = fminf(fmaxf(v, 0.f), 255.f);
   }
 }
+// Input side of the step: what utils/dataloader.py:69-77 does per decoded PNG on the CPU --
+// Pad((0,3,0,3)) with zeros, ToTensor (/255), fn_lognorm255 = log(255 v + 1) / log 256 (utils/norm.py:8-18),
+// UniformNoise(scale) = + scale * U[0,1) (utils/noise.py:32-35, padding rows included), Normalize(0.5, 0.5) --
+// as one pass over a pre-decoded uint8 event tensor: 1 byte in (+ 4 of noise), 4 bytes out per pixel.
+__global__ void event_preprocess_kernel(const uint8_t* img, int64_t n, int h_in, int w, int pad, const float* noise,
+                                        float scale, float* out) {
+  const int h = h_in + 2 * pad;
+  const int64_t total = n * h * (int64_t)w;
+  const float inv_log256 = 0.18033688011112042f;  // 1 / ln 256
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = i % w; const int64_t t = i / w; const int y = t % h; const int64_t nn = t / h;
+    const int ys = y - pad;
+    float v = 0.f;
+    if (ys >= 0 && ys < h_in) v = logf((float)img[(nn * h_in + ys) * (int64_t)w + x] + 1.f) * inv_log256;
+    if (noise) v = fmaf(scale, noise[i], v);
+    out[i] = (v - 0.5f) / 0.5f;
+  }
+}
 }  // namespace
 
 extern "C" {
+int iea_event_preprocess(const uint8_t* img, int64_t n, int h_in, int w, int pad, const float* noise, float scale,
+                         float* out, iea_stream_t st) {
+  IEA_CHECK_ARG(n > 0 && h_in > 0 && w > 0 && pad >= 0, "iea_event_preprocess: bad geometry");
+  event_preprocess_kernel<<<ew_blocks(n * (h_in + 2 * pad) * (int64_t)w), 256, 0, (cudaStream_t)st>>>(
+      img, n, h_in, w, pad, noise, scale, out);
+  return check_launch("iea_event_preprocess");
+}
 int iea_nchw_to_nhwc(const void* src, int sdt, void* dst, int ddt, int64_t n, int c, int64_t hw, iea_stream_t st) {
   dim3 grid(cdiv(hw, 32), cdiv(c, 32), (unsigned)n), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)st>>>(src, sdt, dst, ddt, n, c, hw);

@@ -132,9 +132,10 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
         if gs["graph"] is None:
             gs["calls"] += 1
             if gs["calls"] <= graph_warmup:
-                # warm-up on a SIDE stream (torch's CUDA-graph recipe): autograd binds each parameter's gradient
-                # accumulator to the stream of its first backward, and a capture cannot depend on the legacy
-                # default stream.  Nets whose first backward already ran on the default stream cannot be captured.
+                # warm-up on the SAME side stream the capture will use: autograd binds a parameter's gradient
+                # accumulator node to the stream that was current when the node was built, and at the end of a
+                # backward pass the caller's stream waits for every such leaf stream -- which a capturing stream may
+                # only do for itself ("dependency created on uncaptured work in another stream" otherwise).
                 side = gs.setdefault("side", torch.cuda.Stream())
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
@@ -150,7 +151,7 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
             try:
                 # relaxed: the backward passes stage their job tables through pinned host buffers, and a pinned
                 # allocation (cudaHostAlloc) is an 'unsafe' call under the default global capture mode
-                with torch.cuda.graph(g, capture_error_mode="relaxed"):
+                with torch.cuda.graph(g, stream=gs.setdefault("side", torch.cuda.Stream()), capture_error_mode="relaxed"):
                     gs["vals"] = body(gs["x"], gs["y"])
             finally:
                 engine.GRAPH_KEEP = None

@@ -330,6 +330,13 @@ int iea_loss_unif_fwd(const float* x, int events, int seq, int dim, float t, flo
 int iea_loss_unif_bwd(const float* x, const float* saved, const float* dloss, int events, int seq,
                       int dim, float t, float* dx, iea_stream_t stream);
 
+/* ---- input pipeline: utils/dataloader.py:69-77 on a pre-decoded uint8 event tensor ----
+ * out[n][h_in+2*pad][w] = 2*(log(u8 + 1)/log 256 + scale*noise) - 1 with `pad` zero rows above and below
+ * (Pad((0,3,0,3)) -> ToTensor -> fn_lognorm255 -> UniformNoise(scale) -> Normalize(0.5, 0.5));
+ * noise: U[0,1) draws of the output's shape (torch.rand_like in the reference), or NULL for none. */
+int iea_event_preprocess(const uint8_t* img, int64_t n, int h_in, int w, int pad, const float* noise,
+                         float scale, float* out, iea_stream_t stream);
+
 /* ---- sampling post-process: model.py:1139-1147 (7-ADU cut, 256^x - 1, clamp, crop 3 rows) ---- */
 int iea_adu_postprocess(const float* img, int64_t n, int h, int w, float* out /* [n][h-6][w] */,
                         iea_stream_t stream);

@@ -404,3 +404,14 @@ def generate_postprocess(imgs):
     imgs = F.threshold(imgs, -0.26, -1)
     imgs = torch.pow(256, imgs * 0.5 + 0.5).add(-1).clamp(0, 255)
     return imgs[:, 0, 3:-3, :]
+
+
+def preprocess_events(images_u8, draws=None, scale=4e-3, pad=3):
+    """utils/dataloader.py:69-77 on a decoded uint8 batch (N,H,W): zero-pad `pad` rows top and bottom, ToTensor,
+    fn_lognorm255 (utils/norm.py:8-18), + scale*U[0,1) (utils/noise.py:32-35), Normalize(0.5, 0.5)."""
+    n, h, w = images_u8.shape
+    x = torch.zeros(n, 1, h + 2 * pad, w)
+    x[:, 0, pad:pad + h] = torch.log(255 * (images_u8.float() / 255) + 1) / math.log(256)
+    if draws is not None:
+        x = x + scale * draws
+    return (x - 0.5) / 0.5

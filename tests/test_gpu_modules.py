@@ -211,3 +211,21 @@ def test_module_on_non_current_device(gold):
     assert torch.cuda.current_device() == 0
     y = m(rec["inputs"][0].to("cuda:1"))
     assert y.device.index == 1 and rel(y, rec["outputs"][0]) < 2e-4
+
+
+def test_input_pipeline(gold):
+    """iea_event_preprocess (pad + log-norm + dequantisation noise + normalise on the GPU) against the reference's
+    transform chain; then the prefetcher end to end (shapes, value range, every batch delivered)."""
+    from iea_gan_b200 import pipeline
+    d = gold["pipeline"]
+    got = pipeline.preprocess_events(d["u8"].cuda(), draws=d["draws"].cuda())
+    assert got.shape == d["out"].shape and rel(got, d["out"]) < 1e-6
+    clean = pipeline.preprocess_events(d["u8"].cuda(), scale=0)
+    assert float((clean[:, :, :3] + 1).abs().max()) == 0.0 and float(clean.max()) <= 1.0
+    batches = [((torch.rand(40, 250, 64) ** 8 * 255).to(torch.uint8), torch.arange(40)) for _ in range(3)]
+    seen = 0
+    for x, y in pipeline.EventPrefetcher(batches, "cuda"):
+        assert x.shape == (40, 1, 256, 64) and x.is_cuda and float(x.min()) >= -1.0 and float(x.max()) <= 1.0 + 8e-3
+        assert torch.equal(y.cpu(), torch.arange(40))
+        seen += 1
+    assert seen == 3

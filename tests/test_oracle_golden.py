@@ -155,3 +155,12 @@ def test_train_step_matches_unmodified_train_fns(small_cfg, golden_step):
         assert rel(sg[k], v) < 1e-4, k
     for k, v in golden_step["d_buffers"].items():
         assert rel(sd[k], v) < 1e-4, k
+
+
+def test_input_pipeline_matches_reference_transforms():
+    """oracle.preprocess_events against the reference's own transform chain (utils/dataloader.py:69-77) run on
+    synthetic decoded images by tests/golden/make_golden_modules.py."""
+    d = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "modules.pt"))["pipeline"]
+    got = O.preprocess_events(d["u8"], d["draws"])
+    assert got.shape == d["out"].shape == (6, 1, 256, 48)
+    assert float((got - d["out"]).abs().max()) < 1e-6
