@@ -477,7 +477,7 @@ def bench_train(args, cfg, dev, world, dist_on, ev, K_, W, hbm_peak, graph):
         dp.attach(G)  # end-of-backward all-reduce of the flat gradient buffers: nothing in the step knows about ranks
         dp.attach(D)
     n = 40 * ev
-    tcfg = dict(cfg, batch_size=n)
+    tcfg = dict(cfg, batch_size=n, micro_events=8 if ev > 8 else 0)
     z_ = NormalNoise(n, cfg["dim_z"], dev)
     G_ema = P.Generator(**dict(cfg, skip_init=True, no_optim=True)).to(dev)
     ema = EMA(G, G_ema, cfg["ema_decay"], cfg["ema_start"])
@@ -490,7 +490,7 @@ def bench_train(args, cfg, dev, world, dist_on, ev, K_, W, hbm_peak, graph):
     wt = max(W, 10)
     l0 = E_.LAUNCHES[0]
     ms_t, spread = timed(lambda: train(x, y), K_, wt, dist_on, per_step=True)
-    launches_t = (E_.LAUNCHES[0] - l0) // (K_ + wt)
+    launches_t = getattr(train, "launches_per_step", None) or (E_.LAUNCHES[0] - l0) // (K_ + wt)
     ms_te = timed(lambda: train(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)), K_, 3, dist_on)
     hb = cfg["H_base"]
     tr = {"metric": "G+D train-step events/s (40 PXD imgs/event)", "value": round(ev * world / (ms_t * 1e-3), 3),
@@ -590,6 +590,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sample", choices=["sample", "train", "attn-sweep"])
     ap.add_argument("--events", type=int, default=0, help="events per GPU (default 16 sampling / 8 training)")
+    ap.add_argument("--global-events", type=int, default=0,
+                    help="train: TOTAL events per step over all ranks (strong scaling, BASELINE configs[3]: 64); "
+                         "per-GPU events above 8 are processed as 8-event micro-batches with accumulated gradients")
     ap.add_argument("--hbase", type=int, default=1)
     ap.add_argument("--sweep", default="1,4,16,64,256", help="event counts of --workload attn-sweep")
     ap.add_argument("--no-graph", action="store_true", help="train step launched kernel by kernel instead of as a CUDA graph")
@@ -649,8 +652,17 @@ def main():
         if not args.no_extras:
             line["train_step"] = bench_train(args, cfg, dev, world, dist_on, 8, max(K_, 20), W, hbm_peak, graph)
     else:
-        t = bench_train(args, cfg, dev, world, dist_on, args.events or 8, K_, W, hbm_peak, graph)
+        ev_t = args.events or 8
+        if args.global_events:
+            if args.global_events % world:
+                raise SystemExit("--global-events %d does not split over %d ranks" % (args.global_events, world))
+            ev_t = args.global_events // world
+            common["scaling"] = "strong"
+        t = bench_train(args, cfg, dev, world, dist_on, ev_t, K_, W, hbm_peak, graph)
         line = dict(common, **t)
+        if args.global_events:
+            line["global_events"] = args.global_events
+            line["micro_events"] = 8 if ev_t > 8 else ev_t
         line["config"] = {"workload": "full G+D hinge/contrastive train step with DiffAugment, ortho-reg, clip + Adam, "
                                       "EMA, %d events/GPU, 256x%d" % (t["events_per_gpu"], res_w),
                           "events_per_gpu": t["events_per_gpu"], "H_base": args.hbase, "parallelism": "dp%d" % world,

@@ -71,12 +71,13 @@ class GradSync:
     def __init__(self, group=None):
         self.group = group
         self.pending = False
+        self.enabled = True  # micro-batched steps switch it off for all but the last backward (cf. DDP.no_sync)
         self.count = 0
 
     def after_backward(self, net):
         """Called by the engine at the end of every backward of `net` inside one autograd pass (the
         Discriminator runs twice per D step): queue the all-reduce once, at the end of the pass."""
-        if self.pending:
+        if self.pending or not self.enabled:
             return
         self.pending = True
 

@@ -74,8 +74,25 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
     g_ortho = OrthoReg(g_params, config["G_ortho"], g_black) if config.get("G_ortho", 0.0) > 0.0 else None
     names = ("G_loss", "D_loss_real", "D_loss_fake", "unif_loss_d", "iea_loss")
 
+    micro = int(config.get("micro_events", 0)) * 40  # rows per micro-batch (0: the whole batch at once)
+    syncs = [n_.__dict__.get("_iea_grad_sync") for n_ in (D, G)]
+
+    def set_sync(on):
+        for sy in syncs:
+            if sy is not None:
+                sy.enabled = on
+
     def body(x, y):
-        """One step; returns the (5,) device tensor of reported losses (no host synchronisation inside)."""
+        """One step; returns the (5,) device tensor of reported losses (no host synchronisation inside).
+        With config["micro_events"] = m the batch is processed m events at a time and the gradients accumulate in
+        the flat buffers (one optimizer step, one data-parallel all-reduce per net): same result, bounded memory --
+        how 32 events per GPU (BASELINE configs[3] on 2 GPUs) fit."""
+        n = x.shape[0]
+        mb = micro if 0 < micro < n else n
+        if n % mb:
+            raise ValueError("%d rows do not split into micro-batches of %d" % (n, mb))
+        chunks = [slice(r, r + mb) for r in range(0, n, mb)]
+        w = 1.0 / len(chunks)
         G.optim.zero_grad()
         D.optim.zero_grad()
         toggle_grad(d_params, True)
@@ -83,15 +100,21 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
         t = 1.0
         # ---- D step (train_fns.py:49-139)
         z = z_.sample_()
-        pf, ef, d_fake, pr, er, d_real = GD(z, y, x, y, contra=True, train_G=False, split_D=True,
-                                            diff_aug=config["diff_aug"])
-        l_real, l_fake = losses.loss_hinge_dis(d_fake, d_real)
-        d_loss = l_real + l_fake + config["contra_lambda"] * contra(er, pr, None, y, t, 0)
-        unif_d = torch.zeros((), device=d_loss.device)
-        if use_unif:  # train_fns.py:122-124
-            unif_d = losses.unif_loss(er)
-            d_loss = d_loss + config["unif_lambda"] * unif_d
-        d_loss.backward()
+        ers, rep = [], None
+        for ci, sl in enumerate(chunks):
+            set_sync(ci == len(chunks) - 1)
+            pf, ef, d_fake, pr, er, d_real = GD(z[sl], y[sl], x[sl], y[sl], contra=True, train_G=False, split_D=True,
+                                                diff_aug=config["diff_aug"])
+            l_real, l_fake = losses.loss_hinge_dis(d_fake, d_real)
+            d_loss = l_real + l_fake + config["contra_lambda"] * contra(er, pr, None, y[sl], t, 0)
+            unif_d = torch.zeros((), device=d_loss.device)
+            if use_unif:  # train_fns.py:122-124
+                unif_d = losses.unif_loss(er)
+                d_loss = d_loss + config["unif_lambda"] * unif_d
+            (d_loss * w if len(chunks) > 1 else d_loss).backward()
+            ers.append(er)
+            r = torch.stack([l_real.detach(), l_fake.detach(), unif_d.detach()]) * w
+            rep = r if rep is None else rep + r
         if grad_hook is not None:
             grad_hook(D)
         if d_ortho is not None:  # utils.ortho(D, D_ortho), train_fns.py:133-134
@@ -102,15 +125,20 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
         toggle_grad(g_params, True)
         G.optim.zero_grad()
         z = z_.sample_()
-        pf, ef, d_fake = GD(z, y, contra=True, train_G=True, split_D=True, diff_aug=config["diff_aug"])
-        g_loss = losses.loss_hinge_gen(d_fake) + config["contra_lambda"] * contra(ef, pf, None, y, t, 0)
-        iea_l = torch.zeros((), device=g_loss.device)
-        if use_iea:  # train_fns.py:169-176: the G uniformity term sits INSIDE the IEA branch
-            iea_l = losses.IEA_loss(ef, er)
-            g_loss = g_loss + config["IEA_lambda"] * iea_l
-            if use_unif:
-                g_loss = g_loss + config["unif_lambda"] * losses.unif_loss(ef)
-        g_loss.backward()
+        repg = None
+        for ci, sl in enumerate(chunks):
+            set_sync(ci == len(chunks) - 1)
+            pf, ef, d_fake = GD(z[sl], y[sl], contra=True, train_G=True, split_D=True, diff_aug=config["diff_aug"])
+            g_loss = losses.loss_hinge_gen(d_fake) + config["contra_lambda"] * contra(ef, pf, None, y[sl], t, 0)
+            iea_l = torch.zeros((), device=g_loss.device)
+            if use_iea:  # train_fns.py:169-176: the G uniformity term sits INSIDE the IEA branch
+                iea_l = losses.IEA_loss(ef, ers[ci])
+                g_loss = g_loss + config["IEA_lambda"] * iea_l
+                if use_unif:
+                    g_loss = g_loss + config["unif_lambda"] * losses.unif_loss(ef)
+            (g_loss * w if len(chunks) > 1 else g_loss).backward()
+            r = torch.stack([g_loss.detach(), iea_l.detach()]) * w
+            repg = r if repg is None else repg + r
         if grad_hook is not None:
             grad_hook(G)
         if g_ortho is not None:  # utils.ortho(G, G_ortho, blacklist=G.shared), train_fns.py:185-188
@@ -119,7 +147,7 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
             G.optim.step(clip_norm=config["clip_norm"])
         if ema is not None:
             ema.update(state["itr"])
-        return torch.stack([g_loss.detach(), l_real.detach(), l_fake.detach(), unif_d.detach(), iea_l.detach()])
+        return torch.stack([repg[0], rep[0], rep[1], rep[2], repg[1]])
 
     if not cuda_graph:
         def train(x, y):
@@ -148,6 +176,7 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             engine.GRAPH_KEEP = keep = []  # pinned host tables referenced by captured copies stay alive with the graph
+            l0 = engine.LAUNCHES[0]
             try:
                 # relaxed: the backward passes stage their job tables through pinned host buffers, and a pinned
                 # allocation (cudaHostAlloc) is an 'unsafe' call under the default global capture mode
@@ -156,6 +185,7 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
             finally:
                 engine.GRAPH_KEEP = None
             gs["graph"], gs["keep"] = g, keep
+            train.launches_per_step = engine.LAUNCHES[0] - l0  # kernels of this repo inside one replay
         else:
             gs["x"].copy_(x, non_blocking=True)
             gs["y"].copy_(y, non_blocking=True)
@@ -166,4 +196,5 @@ def make_train_step(G, D, GD, z_, config, ema=None, state=None, grad_hook=None, 
             ema.refresh_hyper(state["itr"])
         gs["graph"].replay()
         return dict(zip(names, gs["vals"].tolist()))
+    train.launches_per_step = None
     return train

@@ -279,3 +279,44 @@ def test_loss_trajectory_bf16_tracks_fp32(small_cfg):
     assert travelled > 0 and float((pa - pb).norm()) < 0.5 * travelled
     print("trajectory: max loss deviation steps 0-11 %.3g, steps 12-19 %.3g; |p_bf16 - p_fp32| / |p_fp32 - p_0| = %.3g"
           % (dev(0, 12), dev(12, 20), float((pa - pb).norm()) / travelled))
+
+
+def test_micro_batched_step_equals_whole_batch(small_cfg):
+    """config["micro_events"]: 4 events processed 2 at a time with gradients accumulating in the flat buffers ==
+    the 4-event step in one go (fp32 activations; only fp32 summation order differs): losses 1e-5, every gradient
+    1e-4, parameters after both optimizer steps 1e-6."""
+    rows = 160
+    cfg = dict(small_cfg, device="cuda", batch_size=rows)
+    phases = draws_for(cfg, 701, rows, 64, 64)
+    torch.manual_seed(702)
+    x = torch.rand(rows, 1, 64, 64) * 2 - 1
+    y = torch.arange(40).repeat(4)
+    res = []
+    for micro in (0, 2):
+        c = dict(cfg, micro_events=micro)
+        # DiffAugment draws are consumed per G_D call: hand each micro-batch its rows of the same draws
+        import iea_gan_b200 as P
+        from iea_gan_b200 import noise
+        from iea_gan_b200.train_step import make_train_step
+        os.environ["IEA_ACT_DTYPE"] = "fp32"
+        try:
+            G, D, _, _ = fresh_nets(c)
+            train = make_train_step(G, D, P.G_D(G, D), FixedZ(phases), c)
+            if micro:
+                chunks = [slice(0, 80), slice(80, 160)]
+                seq = [t for ph in phases for sl in chunks for t in replay_list([ph], sl)]
+            else:
+                seq = replay_list(phases)
+            with noise.replay(seq):
+                losses = train(x.cuda(), y.cuda())
+        finally:
+            os.environ.pop("IEA_ACT_DTYPE", None)
+        res.append((losses, {k: p.grad.clone() for k, p in list(G.named_parameters()) + [("D." + k, p) for k, p in D.named_parameters()]},
+                    torch.cat([p.detach().reshape(-1) for p in list(G.parameters()) + list(D.parameters())])))
+    (la, ga, pa), (lb, gb, pb) = res
+    for k in la:
+        assert abs(la[k] - lb[k]) < 1e-5 * max(1.0, abs(la[k])), (k, la[k], lb[k])
+    scale = max(float(v.norm()) for v in ga.values())
+    bad = [(k, rel(gb[k], ga[k])) for k in ga if float(ga[k].norm()) > 1e-6 * scale and rel(gb[k], ga[k]) > 1e-4]
+    assert not bad, bad[:8]
+    assert rel(pb, pa) < 1e-6
