@@ -227,7 +227,7 @@ def kernel_rooflines(E_, hbm_peak, which):
                           "iea_conv_fprop 16->32 1x1 @256x256 + ccbn/ReLU prologue + up2 residual + stats epilogue "
                           "(thin::conv_thin_kernel), 11 % of the sampling step")
     torch.cuda.empty_cache()
-    out["best"] = one("best", 160, 256, 256, 16, 16, 3, 0,
+    out["best"] = one("best", 640, 256, 256, 16, 16, 3, 0,
                       "iea_conv_fprop 16->16 3x3 @256x256 + ccbn/ReLU prologue + stats epilogue (thin::conv_thin_kernel)")
     torch.cuda.empty_cache()
     return out
@@ -552,6 +552,41 @@ def bench_attn_sweep(args, cfg, dev, hbm_peak, tf_peak):
                          "fwd_GBs": round(byt / ms_f / 1e6, 1), "fwd_frac_hbm_peak": round(byt / ms_f / 1e6 / hbm_peak, 5)})
             del x, xg
     flop = 2 * 40 * 125.8e6
+    # the block as the Discriminator runs it: NHWC bf16 in HBM, no layout conversion (engine-level call)
+    from iea_gan_b200 import engine as E_
+    amods = [att.theta, att.phi, att.g, att.o]
+    grp, hs = E_._mod_plan(att, amods, [E_.act_dtype()] * 4)
+    for b in events:
+        n = 40 * b
+        xn = torch.randn(n, 32, 32 * cfg["H_base"], 256, device=dev).to(E_.act_dtype())
+
+        def fwd_native():
+            grp.run(True, False)
+            return E_._attention(E_.Tape(False), att, E_.Var(xn, need=False), n, 32, 32 * cfg["H_base"], hs)
+
+        def fb_native():
+            tape = E_.Tape(True)
+            grp.run(True, True)
+            xv = E_.Var(xn, need=True)
+            o = E_._attention(tape, att, xv, n, 32, 32 * cfg["H_base"], hs)
+            o.g = xn  # any gradient of the right shape
+            tape.backward()
+        ms_f = _time_call(fwd_native, reps=5 if b < 64 else 3, warm=2)
+        try:
+            ms_b = _time_call(fb_native, reps=3 if b < 64 else 2, warm=1)
+        except torch.OutOfMemoryError:
+            ms_b = float("nan")
+            torch.cuda.empty_cache()
+        byt = 2 * xn.numel() * xn.element_size()
+        rows.append({"op": "attention_c256_32x32_native", "events": b, "fwd_ms": round(ms_f, 4), "fwd_bwd_ms": round(ms_b, 4),
+                     "fwd_events_per_s": round(b / ms_f * 1e3, 1),
+                     "fwd_TFLOPs": round(flop * b / ms_f / 1e9, 3), "fwd_bwd_TFLOPs": round(3 * flop * b / ms_b / 1e9, 3),
+                     "fwd_frac_tensor_peak": round(flop * b / ms_f / 1e9 / tf_peak, 5),
+                     "fwd_GBs": round(byt / ms_f / 1e6, 1), "fwd_frac_hbm_peak": round(byt / ms_f / 1e6 / hbm_peak, 5),
+                     "note": "as inside the Discriminator: NHWC bf16 activations, theta/phi/g/o 1x1 convs + max-pools + "
+                             "tcgen05 attention core + gamma residual"})
+        del xn
+        torch.cuda.empty_cache()
     for b in events:
         n = 40 * b
         x = torch.randn(n, 256, 32, 32 * cfg["H_base"], device=dev)

@@ -254,7 +254,7 @@ def _f32(n, device):
 class SNLayer:
     """One (optionally spectrally-normalised) weight inside an SNGroup."""
     __slots__ = ("mod", "weight", "rows", "cin", "taps", "spectral", "pack_dtype", "wp", "wd", "index",
-                 "colscale", "group", "wd_ld", "shared", "wp_tc", "wd_tc")
+                 "colscale", "group", "wd_ld", "shared", "wp_tc", "wd_tc", "want_tc")
 
     def inv_sigma(self):
         return self.group.cur[0][self.index:self.index + 1]
@@ -283,7 +283,9 @@ class SNGroup:
         self.tables = {}
         self.cur = None
 
-    def add(self, mod, pack_dtype):
+    def add(self, mod, pack_dtype, tc=False):
+        """tc: also keep the bf16 tensor-core packs for a layer whose regular packs are fp32 (the head / RRM linears:
+        with >= TC_LINEAR_MIN_ROWS rows they run as tcgen05 GEMMs, see linear())."""
         w = mod.weight
         l = SNLayer()
         l.mod, l.weight = mod, w
@@ -297,6 +299,7 @@ class SNGroup:
         l.wp = l.wd = l.wp_tc = l.wd_tc = None
         l.wd_ld = l.rows
         l.shared = False
+        l.want_tc = bool(tc)
         self.layers.append(l)
         return l
 
@@ -355,8 +358,8 @@ class SNGroup:
         pad16 = lambda c: (c + 15) // 16 * 16
         for l in ls:
             # output channels may be padded to 16 (the 32->1 output conv of G, the 32->1 dgrad of D's stem)
-            f = (not l.shared) and l.pack_dtype == torch.bfloat16 and tc_ok(pad16(l.cin))
-            b = (not l.shared) and l.pack_dtype == torch.bfloat16 and tc_ok(l.rows)
+            f = (not l.shared) and (l.pack_dtype == torch.bfloat16 or l.want_tc) and tc_ok(pad16(l.cin))
+            b = (not l.shared) and (l.pack_dtype == torch.bfloat16 or l.want_tc) and tc_ok(l.rows)
             nf, nb = al(pad16(l.rows) * pad16(l.cin) * l.taps), al(l.rows * pad16(l.cin) * l.taps)
             tc_offs.append((tc_total if f else None, tc_total + nf if b else None))
             tc_total += (nf + nb) if (f or b) else 0
@@ -707,9 +710,48 @@ def mha_core(tape, qkvv, events, seq, heads, d):
     return vv, att
 
 
-def linear(tape, xv, layer, *, bias=None, in_relu=False, res=None, out_dtype=torch.float32):
-    """F.linear(x, W/sigma, b) [+ residual] on a (rows, K) feature matrix: the 1x1 conv with h=w=1."""
+TC_LINEAR_MIN_ROWS = 2048  # feature matrices with at least this many rows go to the tcgen05 GEMM
+
+
+def _cast(tape, xv, dtype, add=None):
+    """y = dtype(x) [+ add] as one pass (iea_axpby); backward casts the gradient back (and feeds `add`)."""
+    x = xv.t
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    b = add.t if add is not None else x
+    K("iea_axpby", ptr(x), dt(x), 1.0, ptr(b), dt(b), 1.0 if add is not None else 0.0, ptr(y), dt(y), x.numel(), L.stream())
+    yv = Var(y)
+    if tape.record:
+        def bw():
+            if yv.g is None:
+                return
+            if xv.need:
+                g = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+                K("iea_axpby", ptr(yv.g), dt(yv.g), 1.0, ptr(yv.g), dt(yv.g), 0.0, ptr(g), dt(g), g.numel(), L.stream())
+                add_grad(xv, g)
+            if add is not None and add.need:
+                add_grad(add, yv.g if add.g is not None else yv.g.clone())
+        tape.add(bw)
+    return yv
+
+
+def _linear_tc_ok(xv, layer, out_dtype):
     n = xv.t.shape[0]
+    cout, cin = layer.rows, layer.cin
+    return (n >= TC_LINEAR_MIN_ROWS and layer.wp_tc is not None and act_dtype() == torch.bfloat16
+            and conv_impl() != L.IMPL_GENERIC and xv.t.dtype == torch.float32 and out_dtype == torch.float32
+            and xv.c == xv.ld and cin % 64 == 0 and ((cout <= 256 and cout % 16 == 0) or cout % 256 == 0))
+
+
+def linear(tape, xv, layer, *, bias=None, in_relu=False, res=None, out_dtype=torch.float32):
+    """F.linear(x, W/sigma, b) [+ residual] on a (rows, K) feature matrix: the 1x1 conv with h=w=1.
+    Few rows (one to a few dozen events): fp32 CUDA-core kernels (weight-read bound, cluster split-K).  From
+    TC_LINEAR_MIN_ROWS rows on (the 256-event RRM sweep: 10240 x 512 x 1536) the product is a real GEMM and runs
+    on the tcgen05 kernel: bf16 operands, fp32 accumulation in TMEM, fp32 features in and out."""
+    n = xv.t.shape[0]
+    if _linear_tc_ok(xv, layer, out_dtype):
+        yb = conv(tape, _cast(tape, xv, torch.bfloat16), layer, n, 1, 1, 1, bias=bias, in_relu=in_relu,
+                  out_dtype=torch.bfloat16, out_shape=(n, layer.rows))
+        return _cast(tape, yb, torch.float32, add=res)
     return conv(tape, xv, layer, n, 1, 1, 1, bias=bias, in_relu=in_relu, res=res,
                 res_c=layer.rows if res is not None else 0, out_dtype=out_dtype, out_shape=(n, layer.rows))
 
@@ -1130,8 +1172,8 @@ class DPlan:
         add(D.linear0, torch.float32)
         for blk in D.RR_D.layers:
             for m in (blk.self_attn.qkv_proj, blk.self_attn.o_proj, blk.linear_net[0], blk.linear_net[3]):
-                add(m, torch.float32)
-        add(D.linear1, torch.float32)
+                self.h[m] = self.sn.add(m, torch.float32, tc=True)
+        self.h[D.linear1] = self.sn.add(D.linear1, torch.float32, tc=True)
         add(D.embed, torch.float32)
 
 
@@ -1420,7 +1462,7 @@ def _mod_plan(mod, mods, dtypes):
     p = mod.__dict__.get(key)
     if p is None or p[0] != act_dtype():
         grp = SNGroup()
-        hs = {m: grp.add(m, d) for m, d in zip(mods, dtypes)}
+        hs = {m: grp.add(m, d, tc=(d == torch.float32 and m.weight.dim() == 2)) for m, d in zip(mods, dtypes)}
         p = (act_dtype(), grp, hs)
         mod.__dict__[key] = p
     return p[1], p[2]

@@ -229,3 +229,42 @@ def test_input_pipeline(gold):
         assert torch.equal(y.cpu(), torch.arange(40))
         seen += 1
     assert seen == 3
+
+
+def test_rrm_large_batch_tcgen05_linears():
+    """64 events (2560 rows >= engine.TC_LINEAR_MIN_ROWS): the RRM's 512-wide linears run as tcgen05 GEMMs (bf16
+    operands, fp32 accumulation) -- against the fp32 CPU oracle: output 2e-2, input / weight gradients 5e-2; and the
+    same module on 4 events (fp32 CUDA-core path) must agree with the oracle to 2e-4 (the switch is by row count)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import iea_gan_b200.relational as RR
+    import iea_gan_b200.sn_layers as SL
+    from iea_gan_b200 import engine as E
+    from oracle import iea_oracle as O
+    lin = functools.partial(SL.SNLinear, **SN)
+    torch.manual_seed(3)
+    m = RR.RelationalReasoning(num_layers=1, input_dim=512, dim_feedforward=512, which_linear=lin, num_heads=4,
+                               dropout=0.0, hidden_dim=512).train()
+    for b, t_out, t_g in ((64, 2e-2, 5e-2), (4, 2e-4, 2e-3)):
+        assert (40 * b >= E.TC_LINEAR_MIN_ROWS) == (b == 64)
+        sd = {"RR." + k: v.detach().clone() for k, v in m.state_dict().items()}
+        x = torch.randn(b, 40, 512, generator=torch.Generator().manual_seed(b))
+        cot = torch.randn(b, 40, 512, generator=torch.Generator().manual_seed(b + 1))
+        names = ["RR.layers.0.self_attn.qkv_proj.weight", "RR.layers.0.linear_net.3.weight", "RR.layers.0.norm1.weight"]
+        for k in names:
+            sd[k].requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        ref = O.rrm_forward(sd, O._Weights(sd, True, 1e-6), "RR", xr, 4)
+        (ref * cot).sum().backward()
+        mg = RR.RelationalReasoning(num_layers=1, input_dim=512, dim_feedforward=512, which_linear=lin, num_heads=4,
+                                    dropout=0.0, hidden_dim=512).train()
+        mg.load_state_dict(m.state_dict())
+        mg = mg.cuda()
+        xg = x.cuda().requires_grad_(True)
+        out = mg(xg)
+        assert rel(out, ref) < t_out, (b, rel(out, ref))
+        (out * cot.cuda()).sum().backward()
+        assert rel(xg.grad, xr.grad) < t_g, (b, rel(xg.grad, xr.grad))
+        ps = dict(mg.named_parameters())
+        for k in names:
+            assert rel(ps[k[3:]].grad, sd[k].grad) < t_g, (b, k, rel(ps[k[3:]].grad, sd[k].grad))

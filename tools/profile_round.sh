@@ -20,6 +20,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-fi
     python tools/prof_sample.py 16 2 > $O/ncu_sample.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $O/launches_train.csv \
     python tools/prof_train.py 8 2 > $O/ncu_train.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_thin_kernel -s 12 -c 12 -f -o $O/prof_thin \
+ncu --set full --clock-control none --import-source on -k regex:conv_thin_kernel -s 21 -c 2 -f -o $O/prof_thin \
     python tools/prof_sample.py 16 2 > $O/ncu_full.log 2>&1
 ls -la $O | tail -12
