@@ -136,6 +136,7 @@ class Tape:
         self.sn_jobs = []  # deferred W/sigma backward of the layers of this pass: one grouped launch
         self.flat = flat   # optim.FlatGrads of the owning net: parameter gradients are written in place
         self.direct = set()
+        self.sn_targets = set()  # gradient tensors the queued (not yet launched) spectral-norm jobs will write
 
     def add(self, fn):
         if self.record:
@@ -152,9 +153,11 @@ class Tape:
         isg, u_, v_ = saved
         self.sn_jobs.append((gp, nsplit, layer.weight, u_, v_, isg, layer.spectral, dw, layer.rows, layer.cin, layer.taps,
                              beta))
+        self.sn_targets.add(dw.data_ptr())
 
     def flush_sn(self):
         jobs, self.sn_jobs = self.sn_jobs, []
+        self.sn_targets = set()
         if not jobs:
             return
         items = (L.SnBwdItem * len(jobs))()
@@ -193,7 +196,7 @@ class Tape:
                 if g.data_ptr() == fl.ptrs[k]:
                     self.direct.add(k)
                     if accumulate_ok:
-                        if k in self.pgrads:
+                        if fl.ptrs[k] in self.sn_targets:
                             self.flush_sn()  # (two queued jobs of one grouped launch must not write the same tensor)
                         return v, 1.0
         return torch.empty_like(param), 0.0
@@ -221,7 +224,8 @@ class Tape:
             return
         if g.data_ptr() == acc.data_ptr():
             return  # written in place with beta = 1
-        self.flush_sn()  # (an accumulation reads the gradient a queued job has not written yet)
+        if acc.data_ptr() in self.sn_targets:
+            self.flush_sn()  # (the accumulation reads a gradient a queued job has not written yet)
         K("iea_axpby", ptr(g), L.F32, 1.0, ptr(acc), L.F32, 1.0, ptr(acc), L.F32, g.numel(), L.stream())
 
 
