@@ -673,7 +673,7 @@ def main():
                     sweep=rows, clocks=sampler.summary(), gpu_launches=E_.LAUNCHES[0],
                     peaks={"hbm_GBs": hbm_peak, "bf16_TFLOPs_burst": tf_burst, "source": which})
         if rank == 0:
-            print(json.dumps(line))
+            print(json.dumps(line), flush=True)
         return
 
     if args.workload == "sample":
@@ -743,9 +743,18 @@ def main():
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist_on:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: a captured CUDA graph still holds NCCL kernels of this communicator, and
+        # destroying the process group under it aborted rank 0 (SIGABRT) after the line had been printed
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -720,8 +720,17 @@ static int wgrad3_run(const iea_conv_desc* d, const void* g, int g_dtype, int g_
   return 0;
 }
 
+int iea_conv_wgrad_tc_splits(const iea_conv_desc* d, int g_dtype, int g_ld);
+int iea_conv_wgrad_tc(const iea_conv_desc* d, const void* g, int g_dtype, int g_ld, float* gpart, cudaStream_t s);
+// wide low-resolution layers: TMEM-accumulating tcgen05 kernel (conv_wgrad_tc.cu); IEA_WGRAD_TC=0 switches it off
+static int wgrad_tc_splits(const iea_conv_desc* d, int g_dtype, int g_ld) {
+  static const int on = [] { const char* v = getenv("IEA_WGRAD_TC"); return !(v && v[0] == '0'); }();
+  return on ? iea_conv_wgrad_tc_splits(d, g_dtype, g_ld) : 0;
+}
+
 extern "C" int iea_conv_wgrad_mma_slices(const iea_conv_desc* d, int g_dtype, int g_ld) {
   if (const int c1g = iea_conv_c1_wgrad_grid(d, g_dtype, g_ld)) return c1g + 1;  // 1-channel side: conv_c1.cu
+  if (const int st = wgrad_tc_splits(d, g_dtype, g_ld)) return st + 1;
   if (const int g3 = wgrad3_run(d, nullptr, g_dtype, g_ld, nullptr, nullptr, nullptr)) {
     const int64_t total = (int64_t)d->cout * d->ksize * d->ksize * d->cin;
     return g3 + 1 + (int)(((int64_t)g3 * d->cout + total - 1) / total);
@@ -749,6 +758,8 @@ extern "C" int iea_conv_wgrad_mma(const iea_conv_desc* d, const void* g, int g_d
     wg::wgrad_reduce_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>(gpart + total, c1g, total, gpart);
     return check_launch("iea_conv_wgrad_mma(1-channel)");  // 0: the bias gradient was not produced
   }
+  if (wgrad_tc_splits(d, g_dtype, g_ld))  // (0: the bias gradient is not produced by this path)
+    return iea_conv_wgrad_tc(d, g, g_dtype, g_ld, gpart, (cudaStream_t)stream);
   if (const int g3 = wgrad3_run(d, nullptr, g_dtype, g_ld, nullptr, nullptr, nullptr)) {  // macro-tile kernel
     const int64_t total = (int64_t)d->cout * d->ksize * d->ksize * d->cin;
     float* parts = gpart + total;
