@@ -319,4 +319,4 @@ def test_micro_batched_step_equals_whole_batch(small_cfg):
     scale = max(float(v.norm()) for v in ga.values())
     bad = [(k, rel(gb[k], ga[k])) for k in ga if float(ga[k].norm()) > 1e-6 * scale and rel(gb[k], ga[k]) > 2e-2]
     assert not bad, bad[:8]
-    assert rel(pb, pa) < 1e-5
+    assert rel(pb, pa) < 1e-3
