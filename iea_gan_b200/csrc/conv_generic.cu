@@ -313,6 +313,24 @@ __global__ void __launch_bounds__(256) colsum_part(const void* g, int g_dtype, i
     __syncthreads();
   }
 }
+// few rows, many columns (the head linears' bias gradients: 320 x 8192): one thread per column, rows in the loop --
+// the row-split kernel above would put the whole matrix on ONE block (0.7 ms for 10 MB)
+__global__ void __launch_bounds__(256) colsum_wide(const void* g, int g_dtype, int g_ld, int rows, int c, float* out,
+                                                   float beta) {
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc >= c) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int m = 0;
+  for (; m + 3 < rows; m += 4) {
+    a0 += ld_act(g, g_dtype, (int64_t)m * g_ld + cc);
+    a1 += ld_act(g, g_dtype, (int64_t)(m + 1) * g_ld + cc);
+    a2 += ld_act(g, g_dtype, (int64_t)(m + 2) * g_ld + cc);
+    a3 += ld_act(g, g_dtype, (int64_t)(m + 3) * g_ld + cc);
+  }
+  for (; m < rows; ++m) a0 += ld_act(g, g_dtype, (int64_t)m * g_ld + cc);
+  const float t = (a0 + a1) + (a2 + a3);
+  out[cc] = beta != 0.f ? fmaf(beta, out[cc], t) : t;
+}
 __global__ void colsum_final(const float* part, int blocks, int c, float* out, float beta) {
   int cc = blockIdx.x * blockDim.x + threadIdx.x;
   if (cc >= c) return;
@@ -754,6 +772,10 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 extern "C" int iea_colsum(const void* g, int g_dtype, int g_ld, int64_t rows, int c, float* out, float beta,
                           float* scratch, iea_stream_t stream) {
+  if (rows <= 4096 && c >= 256) {
+    colsum_wide<<<cdiv(c, 256), 256, 0, (cudaStream_t)stream>>>(g, g_dtype, g_ld, (int)rows, c, out, beta);
+    return check_launch("iea_colsum(wide)");
+  }
   int blocks = (int)((rows + 511) / 512);
   if (blocks > 296) blocks = 296;
   if (blocks < 1) blocks = 1;
