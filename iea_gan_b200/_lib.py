@@ -52,8 +52,8 @@ class MtChunk(C.Structure):
 
 
 class OrthoItem(C.Structure):
-    _fields_ = [("w", vp), ("grad", vp), ("gram", vp), ("rownorm", vp), ("rows", i32), ("cols", i32), ("tall", i32),
-                ("strength", f32)]
+    _fields_ = [("w", vp), ("grad", vp), ("gram", vp), ("rownorm", vp), ("gram_part", vp), ("rows", i32), ("cols", i32),
+                ("tall", i32), ("strength", f32), ("ksplits", i32), ("pad_", i32)]
 
 
 class AugDraws(C.Structure):
@@ -121,7 +121,7 @@ _SIG = {
     "iea_mt_sqnorm": [vp, i32, vp, vp],
     "iea_mt_adam": [vp, i32, vp, f32, f32, f32, f32, vp, vp, vp],
     "iea_mt_lerp": [vp, i32, vp, vp],
-    "iea_ortho_grouped": [vp, vp, i32, vp, i32, vp, i32, vp],
+    "iea_ortho_grouped": [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp],
 }
 
 _RET64 = {"iea_loss_scratch_floats"}  # sizes come back as int64_t; everything else is an int status

@@ -73,18 +73,34 @@ __global__ void __launch_bounds__(256) ortho_gram_kernel(const iea_ortho_item* i
   const int dim = it.tall ? it.cols : it.rows, kk = it.tall ? it.rows : it.cols;
   const int m0 = t.y * TM, n0 = t.z * TN;
   float acc[4][4];
-  if (it.tall)  // G = W^T W: A[m][k] = W[k][m], B[k][n] = W[k][n]
-    tile_gemm(it.w, 1, it.cols, it.w, it.cols, 1, dim, dim, kk, m0, n0, acc);
-  else          // G = W W^T with the diagonal removed: A[m][k] = W[m][k], B[k][n] = W[n][k]
+  float* dst = it.gram;
+  if (it.tall) {  // G = W^T W: A[m][k] = W[k][m], B[k][n] = W[k][n]; the long K (= rows) is split over t.w CTAs
+    const int per = (kk + it.ksplits - 1) / it.ksplits, k0 = t.w * per;
+    const int kn = kk - k0 < per ? kk - k0 : per;
+    tile_gemm(it.w + (int64_t)k0 * it.cols, 1, it.cols, it.w + (int64_t)k0 * it.cols, it.cols, 1, dim, dim, kn > 0 ? kn : 0, m0, n0, acc);
+    dst = it.gram_part + (int64_t)t.w * dim * dim;
+  } else {        // G = W W^T with the diagonal removed: A[m][k] = W[m][k], B[k][n] = W[n][k]
     tile_gemm(it.w, it.cols, 1, it.w, 1, it.cols, dim, dim, kk, m0, n0, acc);
+  }
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
-      if (m < dim && n < dim) it.gram[(int64_t)m * dim + n] = (!it.tall && m == n) ? 0.f : acc[i][j];
+      if (m < dim && n < dim) dst[(int64_t)m * dim + n] = (!it.tall && m == n) ? 0.f : acc[i][j];
     }
+}
+
+// fixed-order sum of the K-split partial Gram matrices of the tall items (deterministic)
+__global__ void __launch_bounds__(256) ortho_gram_reduce_kernel(const iea_ortho_item* items, const int2* red_tab) {
+  const int2 rt = red_tab[blockIdx.x];  // (item, first element of this block's 256-element span)
+  const iea_ortho_item it = items[rt.x];
+  const int64_t n = (int64_t)it.cols * it.cols, i = rt.y + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int s = 0; s < it.ksplits; ++s) a += it.gram_part[(int64_t)s * n + i];
+  it.gram[i] = a;
 }
 
 __global__ void __launch_bounds__(256) ortho_apply_kernel(const iea_ortho_item* items, const int4* tiles) {
@@ -115,14 +131,17 @@ __global__ void __launch_bounds__(256) ortho_apply_kernel(const iea_ortho_item* 
 }  // namespace
 
 extern "C" int iea_ortho_grouped(const iea_ortho_item* items, const int32_t* rownorm_rows, int n_rownorm_rows,
-                                 const int32_t* gram_tiles, int n_gram_tiles, const int32_t* apply_tiles,
-                                 int n_apply_tiles, iea_stream_t stream) {
+                                 const int32_t* gram_tiles, int n_gram_tiles, const int32_t* reduce_blocks,
+                                 int n_reduce_blocks, const int32_t* apply_tiles, int n_apply_tiles,
+                                 iea_stream_t stream) {
   IEA_CHECK_ARG(n_gram_tiles > 0 && n_apply_tiles > 0, "iea_ortho_grouped: empty tile tables");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_rownorm_rows > 0)
     ortho_rownorm_kernel<<<cdiv((int64_t)n_rownorm_rows * 32, 256), 256, 0, st>>>(
         items, reinterpret_cast<const int2*>(rownorm_rows), n_rownorm_rows);
   ortho_gram_kernel<<<n_gram_tiles, 256, 0, st>>>(items, reinterpret_cast<const int4*>(gram_tiles));
+  if (n_reduce_blocks > 0)
+    ortho_gram_reduce_kernel<<<n_reduce_blocks, 256, 0, st>>>(items, reinterpret_cast<const int2*>(reduce_blocks));
   ortho_apply_kernel<<<n_apply_tiles, 256, 0, st>>>(items, reinterpret_cast<const int4*>(apply_tiles));
   return check_launch("iea_ortho_grouped");
 }

@@ -215,31 +215,37 @@ class OrthoReg:
         dev = ps[0].device
         L.require_device(ps[0])
         items = (L.OrthoItem * len(ps))()
-        geo, gsz, rsz = [], 0, 0
+        geo, gsz, rsz, psz = [], 0, 0, 0
         for p in ps:
             rows, cols = p.shape[0], p.numel() // p.shape[0]
             tall = rows > cols and rows > self.TALL
             d = cols if tall else rows
-            geo.append((rows, cols, tall, d, gsz, rsz))
+            ks = max(1, min(32, rows // 512)) if tall else 1  # the long K of W^T W is split over ks CTAs per tile
+            geo.append((rows, cols, tall, d, gsz, rsz, ks, psz))
             gsz += d * d
             rsz += rows if tall else 0
+            psz += ks * d * d if tall else 0
         gram = torch.empty(max(gsz, 1), dtype=torch.float32, device=dev)
         rn = torch.empty(max(rsz, 1), dtype=torch.float32, device=dev)
-        rn_rows, gt, at = [], [], []
-        for i, (p, (rows, cols, tall, d, go, ro)) in enumerate(zip(ps, geo)):
+        gpart = torch.empty(max(psz, 1), dtype=torch.float32, device=dev)
+        rn_rows, gt, at, rb = [], [], [], []
+        for i, (p, (rows, cols, tall, d, go, ro, ks, po)) in enumerate(zip(ps, geo)):
             it = items[i]
             it.w, it.grad, it.gram = p.data_ptr(), p.grad.data_ptr(), gram.data_ptr() + 4 * go
             it.rownorm = rn.data_ptr() + 4 * ro if tall else None
-            it.rows, it.cols, it.tall, it.strength = rows, cols, int(tall), self.strength
+            it.gram_part = gpart.data_ptr() + 4 * po if tall else None
+            it.rows, it.cols, it.tall, it.strength, it.ksplits = rows, cols, int(tall), self.strength, ks
             if tall:
                 rn_rows += [(i, r) for r in range(rows)]
+                rb += [(i, e) for e in range(0, d * d, 256)]
             td = (d + 63) // 64
-            gt += [(i, a, b, 0) for a in range(td) for b in range(td)]
+            gt += [(i, a, b, k) for a in range(td) for b in range(td) for k in range(ks)]
             at += [(i, a, b, 0) for a in range((rows + 63) // 64) for b in range((cols + 63) // 64)]
         dev_i32 = lambda rows_: torch.tensor(np.array(rows_, dtype=np.int32).reshape(-1), dtype=torch.int32, device=dev)
         self._st = {"key": key, "items": torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(dev),
                     "rn_rows": dev_i32(rn_rows) if rn_rows else None, "n_rn": len(rn_rows), "gt": dev_i32(gt),
-                    "n_gt": len(gt), "at": dev_i32(at), "n_at": len(at), "gram": gram, "rn": rn, "device": dev}
+                    "n_gt": len(gt), "rb": dev_i32(rb) if rb else None, "n_rb": len(rb), "at": dev_i32(at), "n_at": len(at),
+                    "gram": gram, "rn": rn, "gpart": gpart, "device": dev}
         return self._st
 
     @torch.no_grad()
@@ -249,7 +255,7 @@ class OrthoReg:
         st = self._state()
         with torch.cuda.device(st["device"]):
             call("iea_ortho_grouped", ptr(st["items"]), ptr(st["rn_rows"]), st["n_rn"], ptr(st["gt"]), st["n_gt"],
-                 ptr(st["at"]), st["n_at"], L.stream(), launches=3 if st["n_rn"] else 2)
+                 ptr(st["rb"]), st["n_rb"], ptr(st["at"]), st["n_at"], L.stream(), launches=4 if st["n_rn"] else 2)
 
 
 def ortho(model, strength=1e-4, blacklist=None):

@@ -222,15 +222,20 @@ typedef struct iea_ortho_item {
   float* grad;
   float* gram;
   float* rownorm;
+  float* gram_part; /* tall only: ksplits partial d*d Gram matrices (the rows are split over ksplits CTAs) */
   int32_t rows, cols;
   int32_t tall;
   float strength;
+  int32_t ksplits;
+  int32_t pad_;
 } iea_ortho_item;
-/* rownorm_rows: (item, row) pairs of the tall items; gram_tiles / apply_tiles: (item, tile row, tile col, 0)
- * with 64 x 64 tiles of the Gram matrix / of the parameter.  Three launches for the whole net. */
+/* rownorm_rows: (item, row) pairs of the tall items; gram_tiles: (item, tile row, tile col, k split) and
+ * apply_tiles: (item, tile row, tile col, 0) with 64 x 64 tiles of the Gram matrix / of the parameter;
+ * reduce_blocks: (item, first element) per 256-element span of a tall item's Gram matrix (fixed-order sum of
+ * its k-split partials).  Three launches for the whole net (four when it has tall matrices). */
 int iea_ortho_grouped(const iea_ortho_item* items, const int32_t* rownorm_rows, int n_rownorm_rows,
-                      const int32_t* gram_tiles, int n_gram_tiles, const int32_t* apply_tiles,
-                      int n_apply_tiles, iea_stream_t stream);
+                      const int32_t* gram_tiles, int n_gram_tiles, const int32_t* reduce_blocks,
+                      int n_reduce_blocks, const int32_t* apply_tiles, int n_apply_tiles, iea_stream_t stream);
 
 /* ---- layout / elementwise helpers ------------------------------------------------- */
 /* NCHW (src_dtype) <-> NHWC (dst_dtype) */

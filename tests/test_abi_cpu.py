@@ -108,3 +108,26 @@ def test_dropin_module_names(small_cfg):
         sys.path.remove(d)
         for mod in ("model", "layers", "RRM", "diff_aug", "loss"):
             sys.modules.pop(mod, None)
+
+
+def test_fused_adam_is_a_torch_optimizer_with_adams_state_layout():
+    """G.optim / D.optim are optim.FusedAdam: constructor, param_groups and state_dict keys of torch.optim.Adam (the
+    reference's checkpoint code and LR schedulers touch exactly these); stepping on a CPU tensor raises (no fallback)."""
+    import torch
+    from iea_gan_b200.optim import FusedAdam
+    ps = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    opt = FusedAdam(ps, lr=2e-4, betas=(0.0, 0.999), weight_decay=0, eps=1e-6)
+    ref = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
+    assert isinstance(opt, torch.optim.Optimizer)
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad"):
+        assert opt.param_groups[0][k] == ref.param_groups[0][k], k
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=10, eta_min=5e-5)
+    sched.step()
+    assert opt.param_groups[0]["lr"] < 2e-4
+    opt.load_state_dict(opt.state_dict())
+    for p in ps:
+        p.grad = torch.zeros_like(p)
+    with pytest.raises(RuntimeError):
+        opt.step()
+    with pytest.raises(NotImplementedError):
+        FusedAdam(ps, weight_decay=0.1)
