@@ -51,6 +51,12 @@ class MtChunk(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("n", i32), ("tensor", i32)]
 
 
+class Bwd1x1Args(C.Structure):
+    _fields_ = [("g", vp), ("y", vp), ("ds1", vp), ("ds2", vp), ("wd_tc", vp), ("inv_sigma", vp), ("dx", vp), ("wpart", vp),
+                ("dbias", vp), ("dscale", vp), ("dshift", vp), ("scratch", vp), ("rows_per_event", i64), ("g_ld", i32),
+                ("y_ld", i32), ("dx_ld", i32), ("beta", f32)]
+
+
 class OrthoItem(C.Structure):
     _fields_ = [("w", vp), ("grad", vp), ("gram", vp), ("rownorm", vp), ("gram_part", vp), ("rows", i32), ("cols", i32),
                 ("tall", i32), ("strength", f32), ("ksplits", i32), ("pad_", i32)]
@@ -118,13 +124,16 @@ _SIG = {
     "iea_loss_unif_bwd": [vp, vp, vp, i32, i32, i32, f32, vp, vp],
     "iea_adu_postprocess": [vp, i64, i32, i32, vp, vp],
     "iea_event_preprocess": [vp, i64, i32, i32, i32, vp, f32, vp, vp],
+    "iea_conv_bwd1x1_grid": [vp],
+    "iea_conv_bwd1x1_scratch_floats": [vp],
+    "iea_conv_bwd1x1": [vp, vp, vp],
     "iea_mt_sqnorm": [vp, i32, vp, vp],
     "iea_mt_adam": [vp, i32, vp, f32, f32, f32, f32, vp, vp, vp],
     "iea_mt_lerp": [vp, i32, vp, vp],
     "iea_ortho_grouped": [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp],
 }
 
-_RET64 = {"iea_loss_scratch_floats"}  # sizes come back as int64_t; everything else is an int status
+_RET64 = {"iea_loss_scratch_floats", "iea_conv_bwd1x1_scratch_floats"}  # sizes come back as int64_t; everything else is an int status
 _lib = None
 _checked_devices = set()
 

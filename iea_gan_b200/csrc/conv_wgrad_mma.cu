@@ -23,21 +23,6 @@ using namespace tc;
 
 constexpr int PW = 10, PH = 18;
 
-struct FastDiv { uint32_t mul, shr, d; };
-inline FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f; f.d = d;
-  if (d == 1) { f.mul = 0; f.shr = 0; return f; }
-  uint32_t s = 0;
-  while ((1u << s) < d) ++s;
-  f.shr = s;
-  f.mul = (uint32_t)(((1ull << (32 + s)) + d - 1) / d - (1ull << 32));
-  return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
-  if (f.d == 1) return n;
-  const uint32_t t = __umulhi(n, f.mul);
-  return (t + ((n - t) >> 1)) >> (f.shr - 1);
-}
 
 struct Params {
   FastDiv fd_tw, fd_th, fd_hw, fd_w, fd_h;

@@ -136,4 +136,23 @@ __device__ __forceinline__ uint4 load_chunk(const iea_conv_desc& d, int hs, int 
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// division by a launch-time constant as multiply-high + shift (n < 2^31): pixel -> (image, row, column) in the
+// tile loops of the persistent kernels
+struct FastDiv { uint32_t mul, shr, d; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d;
+  if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  f.shr = s;
+  f.mul = (uint32_t)(((1ull << (32 + s)) + d - 1) / d - (1ull << 32));
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  const uint32_t t = __umulhi(n, f.mul);
+  return (t + ((n - t) >> 1)) >> (f.shr - 1);
+}
+
+
 }  // namespace tc

@@ -534,9 +534,76 @@ def conv(tape, xv, layer, n, h, w, k, *, bias=None, in_mode=L.IN_DIRECT, in_relu
                        None, None, 0, 0, 0 if accumulate else -1, dst, dst_ptr, cin, 0, None, wtc=wd_tc)
         K("iea_conv_fprop", C.byref(dd), L.stream())
 
+    def bw_fused_1x1(grid):
+        """The whole backward of a same-resolution 1x1 layer in ONE kernel (iea_conv_bwd1x1): statistics adjoint, weight
+        and bias gradient, data gradient and prologue adjoint -- g, y and x are read once, dx is written once."""
+        g_t = yv.g
+        g_ptr, g_ld = yv.off(g_t), yv.ld
+        a = L.Bwd1x1Args()
+        if yv.ds is not None and res is None:
+            ds1, ds2, rpe_ = yv.ds
+            a.y, a.y_ld, a.ds1, a.ds2, a.rows_per_event = yv.off(), yv.ld, ptr(ds1), ptr(ds2), rpe_
+        elif yv.ds is not None:  # the residual branch needs the statistics-adjusted gradient as a tensor
+            ds1, ds2, rpe_ = yv.ds
+            geff = torch.empty((M, cout), dtype=g_t.dtype, device=dev)
+            K("iea_conv_out_bwd", g_ptr, dt(g_t), g_ld, yv.off(), dt(y), yv.ld, act, ptr(ds1), ptr(ds2), M, rpe_,
+              cout, ptr(geff), dt(geff), L.stream())
+            g_t, g_ptr, g_ld = geff, geff.data_ptr(), cout
+        if a.rows_per_event == 0:
+            a.rows_per_event = 1
+        if res is not None and res.need:
+            rg, beta = _accum_target(res)
+            K("iea_residual_bwd", g_ptr, dt(g_t), g_ld, n, h, w, res_c, res_mode, res.off(rg), dt(rg), res.ld,
+              res.c, beta, L.stream())
+        if yv.sc_var is not None:
+            yv.sc_var.g = g_t
+        l = wls[0]
+        isg, u_, v_ = saved[0]
+        need_w = l.weight.requires_grad
+        need_db = bias is not None and bias.requires_grad and need_w
+        kdim = cin
+        keep = [g_t]
+        a.g, a.g_ld, a.wd_tc, a.inv_sigma = g_ptr, g_ld, ptr(wd_tc), ptr(isg)
+        if need_w:
+            wpart = torch.empty((grid + 1) * cout * kdim + grid * cout, dtype=torch.float32, device=dev)
+            a.wpart = ptr(wpart)
+            keep.append(wpart)
+            if need_db:
+                db = tape.galloc(bias)[0]
+                a.dbias = ptr(db)
+        if xv.need:
+            xg, beta = _accum_target(xv)
+            a.dx, a.dx_ld, a.beta = xv.off(xg), xv.ld, beta
+        if ss is not None:
+            dsc, dsh = torch.empty_like(ss.scale), torch.empty_like(ss.shift)
+            ss.dscale, ss.dshift = dsc, dsh
+            dfw0 = fwd_desc()
+            scr = _f32(call("iea_conv_bwd1x1_scratch_floats", C.byref(dfw0)), dev)
+            a.dscale, a.dshift, a.scratch = ptr(dsc), ptr(dsh), ptr(scr)
+        dfw = fwd_desc()
+        K("iea_conv_bwd1x1", C.byref(dfw), C.byref(a), L.stream(), launches=1 + (2 if need_db else 1 if need_w else 0) + (1 if ss is not None else 0))
+        if need_w:
+            dw, beta_w = tape.galloc(l.weight, accumulate_ok=True)
+            tape.sn_weight_bwd(wpart[:cout * kdim].view(1, cout, kdim), 1, l, (isg, u_, v_), dw, beta_w)
+            tape.pgrad(l.weight, dw)
+            if need_db:
+                tape.pgrad(bias, db)
+        elif bias is not None and bias.requires_grad:
+            db = tape.galloc(bias)[0]
+            K("iea_colsum", g_ptr, dt(g_t), g_ld, M, cout, ptr(db), 0.0, ptr(_f32(300 * cout, dev)), L.stream(), launches=2)
+            tape.pgrad(bias, db)
+
     def bw():
         if yv.g is None:
             return
+        if (k == 1 and in_mode == L.IN_DIRECT and grouped is None and act == L.ACT_NONE and wd_tc is not None
+                and yv.g.dtype == torch.bfloat16 and xv.t.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+                and conv_impl() != L.IMPL_GENERIC and (xv.need or ss is not None or wls[0].weight.requires_grad)
+                and (res is None or dt(res.t) == L.BF16) and _env(b"IEA_BWD1X1", "IEA_BWD1X1", "1") != "0"):
+            dfq = fwd_desc()
+            grid = call("iea_conv_bwd1x1_grid", C.byref(dfq))
+            if grid > 0:
+                return bw_fused_1x1(grid)
         g_t = yv.g
         g_ptr, g_ld = yv.off(g_t), yv.ld
         if yv.ds is not None or act == L.ACT_TANH:

@@ -186,6 +186,35 @@ int iea_bn_finalize_bwd(const float* dscale, const float* dshift, const float* s
 int iea_affine_act(const void* x, int x_dtype, const float* scale, const float* shift, int64_t n,
                    int64_t hw, int c, int relu, void* y, int y_dtype, iea_stream_t stream);
 
+/* ---- the whole backward of a 1x1 SNConv2d layer in one kernel (csrc/conv_bwd1x1.cu) ----
+ * Replaces, for same-resolution 1x1 layers with Cin, Cout in {16, 32, 64, 128} and whole 128-pixel tiles per image,
+ * the sequence iea_conv_out_bwd -> iea_conv_wgrad_mma -> iea_conv_fprop(dgrad pack) -> iea_conv_input_bwd:
+ *   geff = g + ds1[e][co] + 2 y ds2[e][co]  (ds1 == NULL: geff = g);   dW += geff^T . T(x),  db += colsum(geff);
+ *   da = geff . W / sigma;  gm = da * 1[x*scale+shift > 0];  dx = beta*dx + gm*scale;
+ *   dscale[n][c] = sum_px gm * x,  dshift[n][c] = sum_px gm.
+ * `fwd` is the FORWARD descriptor of the layer (x, x_ld, cin, cout, in_scale / in_shift / in_relu / in_bcast). */
+typedef struct iea_bwd1x1_args {
+  const void* g;           /* dL/dy rows, bf16 */
+  const void* y;           /* forward output rows, bf16 (read only when ds1 != NULL) */
+  const float* ds1;        /* [events][cout] or NULL */
+  const float* ds2;
+  const void* wd_tc;       /* iea_sn_layer.pack_tc_dgrad of the layer */
+  const float* inv_sigma;  /* 1/sigma of the forward call (NULL: 1) */
+  void* dx;                /* bf16 rows of the input gradient, or NULL */
+  float* wpart;            /* NULL: no weight gradient.  Else (grid+1)*cout*cin + grid*cout floats; slice 0 receives dW */
+  float* dbias;            /* [cout] or NULL (needs wpart) */
+  float* dscale;           /* [n][cin] or NULL */
+  float* dshift;
+  float* scratch;          /* iea_conv_bwd1x1_scratch_floats(fwd) floats when dscale != NULL */
+  int64_t rows_per_event;
+  int32_t g_ld, y_ld, dx_ld;
+  float beta;
+} iea_bwd1x1_args;
+/* > 0: the layer is handled and this is the CTA count `grid` that sizes wpart; 0: use the unfused sequence */
+int iea_conv_bwd1x1_grid(const iea_conv_desc* fwd);
+int64_t iea_conv_bwd1x1_scratch_floats(const iea_conv_desc* fwd);
+int iea_conv_bwd1x1(const iea_conv_desc* fwd, const iea_bwd1x1_args* args, iea_stream_t stream);
+
 /* ---- optimizer step: clip + Adam + EMA as multi-tensor kernels ----- */
 /* One <= 65536-element slice of one tensor.  p: parameter (updated in place); g: its gradient;
  * m, v: Adam's exp_avg / exp_avg_sq; ema: the moving-average copy of p (NULL: none).

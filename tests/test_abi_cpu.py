@@ -46,16 +46,17 @@ def test_version_and_error_channel(lib):
 
 def test_struct_layouts_match_the_header(lib):
     """sizeof of the four POD structs, measured by compiling the header with gcc."""
-    code = '#include <stdio.h>\n#include "iea_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(iea_sn_layer), ' \
+    code = '#include <stdio.h>\n#include "iea_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(iea_sn_layer), ' \
            'sizeof(iea_conv_desc), sizeof(iea_aug_draws), sizeof(iea_sn_bwd_item), sizeof(iea_mt_chunk), ' \
-           'sizeof(iea_ortho_item));return 0;}\n'
+           'sizeof(iea_ortho_item), sizeof(iea_bwd1x1_args));return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         src, exe = os.path.join(td, "s.c"), os.path.join(td, "s")
         open(src, "w").write(code)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(t) for t in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(lib.SnLayer), ctypes.sizeof(lib.ConvDesc), ctypes.sizeof(lib.AugDraws),
-                     ctypes.sizeof(lib.SnBwdItem), ctypes.sizeof(lib.MtChunk), ctypes.sizeof(lib.OrthoItem)]
+                     ctypes.sizeof(lib.SnBwdItem), ctypes.sizeof(lib.MtChunk), ctypes.sizeof(lib.OrthoItem),
+                     ctypes.sizeof(lib.Bwd1x1Args)]
 
 
 def test_no_cpu_fallback(small_cfg):

@@ -427,3 +427,93 @@ def test_skinny_linear_cluster_splitk(eng, rows, cin, cout, xdt, aff, relu, res)
         ref = ref + r
     torch.cuda.synchronize()
     assert rel(y, ref) < 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,hw,relu,aff,ds,resm,beta", [
+    (64, 16, (64, 64), True, True, True, None, 0), (16, 64, (64, 64), True, True, True, 0, 0),
+    (32, 32, (32, 64), True, False, False, None, 1), (128, 32, (32, 32), True, True, True, None, 0),
+    (32, 128, (64, 32), False, False, False, None, 0), (64, 64, (32, 32), True, True, False, None, 1),
+    (16, 16, (128, 64), True, True, True, None, 0),
+    # one shared slot (two producer groups on it), in-place ReLU with the statistics adjoint, affine without ReLU
+    (128, 64, (32, 32), True, True, True, None, 0), (64, 32, (32, 64), True, False, True, None, 0),
+    (16, 32, (64, 64), False, True, True, None, 1)])
+def test_fused_1x1_backward_vs_torch(eng, cin, cout, hw, relu, aff, ds, resm, beta):
+    """iea_conv_bwd1x1 (statistics adjoint + weight / bias gradient + data gradient + prologue adjoint of a 1x1 layer
+    in one tcgen05 kernel) against torch autograd, through engine.conv's backward: dx (also accumulated onto an
+    existing gradient), dW (through the spectral-norm backward), db, dscale / dshift, the residual gradient.
+    Tolerance 2.5e-2 relative L2 (bf16 operands, fp32 accumulation), as the unfused bf16 path."""
+    os.environ["IEA_ACT_DTYPE"] = "bf16"
+    try:
+        dev = "cuda"
+        at = torch.bfloat16
+        torch.manual_seed(3)
+        n, (h, w) = 40, hw
+        m = make_sn_conv(cin, cout, 1, dev)
+        m.train()
+        x = torch.randn(n, cin, h, w, device=dev)
+        xq = x.to(at).float()
+        scale = (torch.rand(n, cin, device=dev) + 0.5) if aff else None
+        shift = torch.randn(n, cin, device=dev) * 0.3 if aff else None
+        Wt = m.weight.detach().clone().requires_grad_(True)
+        bt = m.bias.detach().clone().requires_grad_(True)
+        W2 = Wt.reshape(cout, -1)
+        with torch.no_grad():
+            v = F.normalize(m.u0.clone() @ W2, eps=1e-6)
+            un = F.normalize(v @ W2.t(), eps=1e-6)
+        sig = ((v @ W2.t()) @ un.t()).squeeze()
+        xr = xq.clone().requires_grad_(True)
+        sr = scale.clone().requires_grad_(True) if aff else None
+        hr = shift.clone().requires_grad_(True) if aff else None
+        a = _ref_T(xr, sr, hr, relu, 0)
+        Wq = Wt.detach().to(at).float()
+        yref = F.conv2d(a, (Wq + (Wt - Wt.detach())) / sig, bt)
+        if resm is not None:
+            r = torch.randn(n, cout + 8, h, w, device=dev)
+            rr = r.to(at).float().clone().requires_grad_(True)
+            yref = yref + rr[:, :cout]
+        grp = eng.SNGroup()
+        l = grp.add(m, at)
+        grp.run(True, True)
+        tape = eng.Tape(True)
+        xv = eng.Var(x.permute(0, 2, 3, 1).contiguous().to(at))
+        ss = eng.ScaleShift(scale.contiguous(), shift.contiguous()) if aff else None
+        resv = eng.Var(r.permute(0, 2, 3, 1).contiguous().to(at)) if resm is not None else None
+        yv = eng.conv(tape, xv, l, n, h, w, 1, bias=m.bias, in_relu=relu, ss=ss, res=resv, res_mode=0,
+                      res_c=cout if resm is not None else 0, stats=True)
+        yq = yv.t.float().permute(0, 3, 1, 2)
+        assert rel(yq, yref) < 1.5e-2
+        # loss = sum(y * gy) + a function of the per-event batch statistics of y (what a following batch-norm adds):
+        # sum_c (a1[c] * sum_px y + a2[c] * sum_px y^2)  ->  dL/dy = gy + a1 + 2 y a2 = exactly the (ds1, ds2) adjoint
+        gy = torch.randn_like(yref)
+        loss = (yref * gy).sum()
+        if ds:
+            a1, a2 = torch.randn(1, cout, device=dev) * 0.1, torch.randn(1, cout, device=dev) * 0.05
+            yd = yq.detach()  # the kernel uses the stored (bf16) y in the 2*y*ds2 term
+            loss = loss + (yref * (a1.view(1, cout, 1, 1) + 2 * yd * a2.view(1, cout, 1, 1))).sum()
+        loss.backward()
+        yv.g = gy.permute(0, 2, 3, 1).contiguous().to(at)
+        if ds:
+            yv.ds = (a1.contiguous(), a2.contiguous(), n * h * w)
+        g0 = None
+        if beta:
+            g0 = torch.randn(n, h, w, cin, device=dev).to(at)
+            xv.g = g0.clone()
+        tape.backward()
+        torch.cuda.synchronize()
+        want_dx = xr.grad + (g0.float().permute(0, 3, 1, 2) if beta else 0)
+        assert rel(xv.g.float().permute(0, 3, 1, 2), want_dx) < 2.5e-2
+        assert rel(tape.pgrads[id(m.weight)], Wt.grad) < 2.5e-2
+        assert rel(tape.pgrads[id(m.bias)], bt.grad) < 2.5e-2
+        if aff:
+            assert rel(ss.dscale, sr.grad) < 2.5e-2
+            assert rel(ss.dshift, hr.grad) < 2.5e-2
+        if resm is not None:
+            assert rel(resv.g.float().permute(0, 3, 1, 2)[:, :cout], rr.grad[:, :cout]) < 2.5e-2
+        # and the kernel really was the fused one
+        import ctypes as C
+        dq = eng._desc(n, h, w, cin, cout, 1, xv.t, xv.off(), xv.ld, 0, relu, scale, shift, l.wp, None, 0, None, None, 0, 0,
+                       -1, yv.t, yv.off(), yv.ld, 0, None)
+        from iea_gan_b200 import _lib as L
+        assert L.call("iea_conv_bwd1x1_grid", C.byref(dq)) > 0
+    finally:
+        os.environ.pop("IEA_ACT_DTYPE", None)
