@@ -249,6 +249,10 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
     // chunk cc; its global element offset from the tile's base pixel and its smem offset never change, so an
     // interior tile costs one 64-bit add + one cp.async per chunk (nearest-up2 is folded into the offsets:
     // tile origins are even, hence (h0 - 1 + pi) >> 1 == h0/2 + ((pi - 1) >> 1)).
+    // 2x2-average-pooled input of a 1x1 layer (every DBlock's conv4 / shortcut): a tile of 128 output pixels is whole
+    // rows (or a piece of one row) of one image, so the four source pixels of slot i sit at fixed offsets from the
+    // tile's first source pixel as well -- all loads of an item are issued before the first use, no index arithmetic.
+    const bool pool_fast = pool && !IS3 && !affine && p.uniform_n && (d.w % BM == 0 || BM % d.w == 0);
     int dlt[NL];
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
@@ -256,6 +260,9 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
       if (IS3) {
         const int pi = pp / PW, pj = pp - pi * PW;
         dlt[i] = (((pi - 1) >> sh_) * p.ws + ((pj - 1) >> sh_)) * d.x_ld;
+      } else if (pool_fast) {
+        const int pr = pp / d.w, pc = pp - pr * d.w;
+        dlt[i] = (pr * 2 * p.ws + pc * 2) * d.x_ld;
       } else {
         dlt[i] = pp * d.x_ld;
       }
@@ -357,7 +364,44 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
       const Cur& c = ct_;
       const int ci = c.kb * p.KB + cc * 8;
       uint8_t* a1 = smem + (a_thr - sbase) + c.s * p.stage_bytes;
-      if (slow) {
+      if (pool_fast) {
+        const unsigned m0u = (unsigned)(tile0 + c.tl) * BM, r0 = m0u / (unsigned)d.w, ow0 = m0u - r0 * (unsigned)d.w;
+        const bf16* bp = xb + ((int64_t)r0 * 2 * p.ws + 2 * ow0) * d.x_ld + ci;
+        const int64_t o1 = d.x_ld, o2 = (int64_t)p.ws * d.x_ld;
+#pragma unroll
+        for (int i0 = 0; i0 < NL; i0 += 2) {  // two slots (eight 16-byte loads) in flight per thread
+          uint4 r[2][4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u;
+            if (i < NL && (i < NL - 1 || last_ok)) {
+              const bf16* q = bp + dlt[i];
+              r[u][0] = __ldg(reinterpret_cast<const uint4*>(q));
+              r[u][1] = __ldg(reinterpret_cast<const uint4*>(q + o1));
+              r[u][2] = __ldg(reinterpret_cast<const uint4*>(q + o2));
+              r[u][3] = __ldg(reinterpret_cast<const uint4*>(q + o2 + o1));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u;
+            if (i < NL && (i < NL - 1 || last_ok)) {
+              float acc[8], f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                unpack8(r[u][q], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += relu ? fmaxf(f[j], 0.f) : f[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+              *reinterpret_cast<uint4*>(a1 + i * GP * 16) = pack8(acc);
+            }
+          }
+        }
+      } else if (slow) {
         const Origin o = origin_of<IS3>(c.t, tile0 + c.tl);
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
