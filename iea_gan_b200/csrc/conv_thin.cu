@@ -26,6 +26,7 @@ namespace thin {
 using namespace tc;
 
 constexpr int BM = 128;
+constexpr int RES_RING = 4;    // residual sub-tiles in flight per epilogue group (TMA-store flavour)
 constexpr int THREADS = 512;  // warps 0-7: two producer groups (they also issue their tiles' MMAs), warps 8-15: two epilogue groups
                               // (one CTA per SM; the groups take alternate macro tiles so every hand-off latency is
                               // covered by the other group's tile)
@@ -71,7 +72,7 @@ struct Params {
   int mtw, mth;           // macro tiles per image row / per image column (1x1: per image / 1)
   int hs, ws;             // stored input resolution
   int stages, depth, dbg;
-  uint32_t w_bytes, stage_off, misc_off, bar_off, tmem_cols;
+  uint32_t w_bytes, stage_off, misc_off, bar_off, tmem_cols, tst_off, res_off, res_slot;  // tst_off: output staging of the TMA-store epilogue; res_off / res_slot: its residual ring
 };
 
 struct Pos { int n, th, tw; };
@@ -120,14 +121,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // EPI: epilogue flavour, fixed at compile time so that each is straight-line code (run-time flags made the
 // compiler shuffle the 16 accumulator registers at every merge point: ~200 instructions per 128x16 block
 // where ~70 do the work).  1: scale/bias + residual read, same-resolution or nearest-up2 [+ statistics]
-// (the GBlock conv4 layers);  2: everything (pooled residual, accumulate, activation, padded 1-channel store)
+// (the GBlock conv4 layers);  2: everything (pooled residual, accumulate, activation, padded 1-channel store);
+// 3: flavour 1 with the output leaving through TMA: one pixel per thread means a warp's 16-byte stores hit 16 different
+// 128-byte lines per instruction, and those wavefronts (not HBM, not the math) kept the L1 data pipe of the dominant
+// launch 55 % busy.  The group writes its 128 x 64 B (or 32 B) sub-tile into a swizzled shared-memory image
+// (conflict-free) and one thread hands it to the TMA unit, which writes whole lines.
 // TMA: same-resolution inputs are fetched by TMA box loads, one per 8-channel plane ({8 ch, patch width, 18 rows}
 // for 3x3 with out-of-image pixels zero-filled by the unit; {8 ch, 128 pixels} for 1x1): one elected thread per
 // producer group issues them, the other producer threads only run the fused prologue (nothing at all for the
 // prologue-free data-gradient convolutions).  Nearest-up2 inputs keep the cp.async slot tables.
 template <int CPR, bool IS3, int NB, int MT, int EPI, bool TMA>
 __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_constant__ Params p,
-                                                               const __grid_constant__ CUtensorMap tmap) {
+                                                               const __grid_constant__ CUtensorMap tmap,
+                                                               const __grid_constant__ CUtensorMap tmap_y,
+                                                               const __grid_constant__ CUtensorMap tmap_r) {
   using G = Geo<CPR, IS3, MT, TMA>;
   constexpr int PW = G::PW, NCH = G::NCH, NS = G::NS;
   constexpr uint32_t PLANE = G::PLANE, STAGE = G::STAGE;
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
     for (int b = 0; b < 4; ++b) { mbar_init(tfull0 + 8 * b, NI); mbar_init(tempty0 + 8 * b, 4); }
     mbar_init(w_bar, 1);
     if (TMA) for (int s = 0; s < S; ++s) mbar_init(land0 + 8 * s, 1);
+    if (EPI == 3) for (int i = 0; i < 2 * RES_RING; ++i) mbar_init(bar0 + 24u * S + 80 + 8 * i, 1);  // residual ring: TMA landing
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -411,7 +419,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       else asm volatile("bar.sync 2, 128;" ::: "memory");
     };
     const bool has_stats = d.stats != nullptr;
-    const bool has_res = EPI == 1 ? true : (EPI == 2 ? d.res != nullptr : false);
+    constexpr bool TST = EPI == 3;  // TMA store of the output sub-tiles
+    const bool has_res = (EPI == 1 || EPI == 3) ? true : (EPI == 2 ? d.res != nullptr : false);
     const bool res_pool = EPI == 2 && d.res_mode == IEA_IN_POOL2;
     const bool res_up2 = EPI >= 1 && d.res_mode == IEA_IN_UP2;
     const bool need_px = IS3 || (has_res && d.res_mode != IEA_IN_DIRECT);
@@ -456,6 +465,41 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
     const bf16* const rp = (const bf16*)d.res;
     bool any = false;
     const int64_t ystep = (int64_t)(IS3 ? 8 : BM) * d.y_ld;
+    // TMA-store staging: two sub-tile images per group, rows of RB bytes, 16-byte chunks XOR-swizzled like the
+    // tensor map (64B / 32B swizzle) so that the row-per-thread writes are conflict-free
+    constexpr uint32_t RB = BN * 2, ST_IMG = BM * RB;
+    const uint32_t st_al = ((sbase + p.tst_off + 1023u) & ~1023u) - sbase;  // (the swizzle works on absolute addresses)
+    const uint32_t st_u32 = sbase + st_al + grp * (2 * ST_IMG);
+    uint8_t* const st_ptr = smem + st_al + grp * (2 * ST_IMG);
+    const int st_sw = NB == 2 ? ((et >> 1) & 3) : ((et >> 2) & 1);
+    int st_cnt = 0;
+    // ... and the residual ENTERS through TMA as well: the rows of a sub-tile (64 source pixels for a nearest-up2
+    // residual, 128 otherwise; <= 64 bytes each, swizzled) land in a ring slot RES_RING sub-tiles ahead of their use.
+    // The per-pixel 16-byte loads they replace were an exposed L2 round trip per 16-channel block: 45 % of the
+    // epilogue's time on the dominant launch.
+    const uint32_t rr_al = ((sbase + p.res_off + 1023u) & ~1023u) - sbase;
+    const uint32_t rr_u32 = sbase + rr_al + grp * (RES_RING * p.res_slot), rr_bar = bar0 + 24u * S + 80 + grp * (RES_RING * 8);
+    const uint8_t* const rr_ptr = smem + rr_al + grp * (RES_RING * p.res_slot);
+    const int rr_sub = my_n > grp ? ((my_n - grp + 1) >> 1) * MT : 0;  // sub-tiles of this group
+    const uint32_t rr_rb = (uint32_t)d.res_c * 2;                       // bytes per residual row (64 or 32)
+    const int rr_row = res_up2 ? (et >> 1) : et;
+    const uint8_t* const rr_mine = rr_ptr + rr_row * rr_rb;
+    const int rr_sw = rr_rb == 64 ? ((rr_row >> 1) & 3) : ((rr_row >> 2) & 1);
+    auto rr_issue = [&](int sidx) {  // one thread: TMA load of the residual rows of this group's sub-tile `sidx`
+      if (sidx >= rr_sub) return;
+      const int msub = (g0 + grp + 2 * (sidx / MT)) * (BM * MT) + (sidx % MT) * BM;
+      int src0 = msub;
+      if (res_up2) {
+        const unsigned r1 = fdiv((unsigned)msub, p.fd_w);
+        src0 = (int)(r1 >> 1) * (d.w >> 1) + (int)(((unsigned)msub - r1 * (unsigned)d.w) >> 1);
+      }
+      const uint32_t bar = rr_bar + 8 * (sidx % RES_RING);
+      mbar_expect_tx(bar, (res_up2 ? 64u : 128u) * rr_rb);
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                   ::"r"(rr_u32 + (sidx % RES_RING) * p.res_slot), "l"(reinterpret_cast<uint64_t>(&tmap_r)), "r"(0), "r"(src0), "r"(bar) : "memory");
+    };
+    if (TST && et == 0)
+      for (int i = 0; i < RES_RING; ++i) rr_issue(i);
     for (int t = grp; t < my_n; t += 2) {
       const uint32_t ab = t & 3, aph = (t >> 2) & 1;
       int m0, oh = 0, ow0 = 0;
@@ -476,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       }
       // residual rows are pulled into L1 one batch of sub-tiles ahead of their use (prefetch: no registers),
       // so the loads below do not stall every sub-tile on an L2 / HBM round trip
-      const bool res_l1 = !IS3 && has_res && !res_pool;
+      const bool res_l1 = !TST && !IS3 && has_res && !res_pool;
       auto res_prefetch = [&](int m) {
         if (m >= p.M) return;
         const bf16* sp;
@@ -523,14 +567,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
           const bool valid = IS3 || m < p.M;
           if (!valid) continue;  // (the aligned tcgen05.ld of this batch are already done)
           int rn = nn, roh = oh, row = ow0 + sb * 8;
-          if (!IS3 && need_px) {
+          if (!TST && !IS3 && need_px) {
             const unsigned t1 = fdiv((unsigned)m, p.fd_w);
             row = (int)((unsigned)m - t1 * (unsigned)d.w); rn = (int)fdiv(t1, p.fd_h); roh = (int)(t1 - (unsigned)rn * (unsigned)d.h);
           }
           const bf16* rsp = nullptr;  // this pixel's residual row (same resolution / nearest-up2 source pixel)
-          if (has_res && !res_pool)
+          if (!TST && has_res && !res_pool)
             rsp = res_up2 ? rp + (((int64_t)rn * (d.h >> 1) + (roh >> 1)) * (d.w >> 1) + (row >> 1)) * d.res_ld
                           : rp + (int64_t)m * d.res_ld;
+          const uint8_t* rr_slot = rr_mine + (st_cnt % RES_RING) * p.res_slot;
+          if (TST) mbar_wait(rr_bar + 8 * (st_cnt % RES_RING), (st_cnt / RES_RING) & 1);  // this sub-tile's residual rows
 #pragma unroll
           for (int cb = 0; cb < NB; ++cb) {
             const int c0 = cb * 16;
@@ -564,7 +610,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
                     for (int j = 0; j < 8; ++j) v[j] = ffma2(bf2_to_f2(w[j]), quarter, v[j]);
                   }
               } else {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(rsp + c0), r1 = *reinterpret_cast<const uint4*>(rsp + c0 + 8);
+                uint4 r0, r1;
+                if (TST) {
+                  r0 = *reinterpret_cast<const uint4*>(rr_slot + (((2 * cb) ^ rr_sw) << 4));
+                  r1 = *reinterpret_cast<const uint4*>(rr_slot + (((2 * cb + 1) ^ rr_sw) << 4));
+                } else {
+                  r0 = *reinterpret_cast<const uint4*>(rsp + c0);
+                  r1 = *reinterpret_cast<const uint4*>(rsp + c0 + 8);
+                }
                 const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fadd2(v[j], bf2_to_f2(w[j]));
@@ -594,7 +647,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
             uint32_t o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = pack2(v[j].x, v[j].y);
-            if (!DBG(4)) {
+            if (TST) {
+              uint8_t* row_ = st_ptr + (st_cnt & 1) * ST_IMG + et * RB;
+              *reinterpret_cast<uint4*>(row_ + (((2 * cb) ^ st_sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(row_ + (((2 * cb + 1) ^ st_sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            } else if (!DBG(4)) {
               yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
               yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
             }
@@ -602,6 +659,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
 #pragma unroll
               for (int j = 0; j < 8; ++j) { s1[cb * 8 + j] = fadd2(s1[cb * 8 + j], v[j]); s2[cb * 8 + j] = ffma2(v[j], v[j], s2[cb * 8 + j]); }
             }
+          }
+          if (TST) {  // the sub-tile image is complete: hand it to the TMA unit (host guarantees whole sub-tiles)
+            fence_async_smem();
+            // the OTHER image, which the group writes next, must have been read by its store (issued a sub-tile ago)
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            bar_grp();
+            if (et == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmap_y)), "r"(0), "r"(m - et), "r"(st_u32 + (st_cnt & 1) * ST_IMG) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              rr_issue(st_cnt + RES_RING);  // (every thread of the group is past its reads of this slot: bar_grp above)
+            }
+            ++st_cnt;
           }
         }
       }
@@ -611,6 +681,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_thin_kernel(const __grid_cons
       if (et == 0) TRACE(7, t);
     }
     if (has_stats && any) flush(ev);
+    if (TST && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -673,6 +744,34 @@ static encode_tiled_fn tma_encoder() {
   }
   return fn;
 }
+// output of a 1x1 layer as {cout channels, pixels}: boxes {cout, 128}, chunks swizzled inside the 64 / 32-byte rows
+static bool thin_tensor_map_y(const iea_conv_desc* d, CUtensorMap* tm) {
+  encode_tiled_fn enc = tma_encoder();
+  if (!enc || d->y_dtype != IEA_BF16 || d->y_ld % 8 || ((uintptr_t)d->y & 15) || (d->cout != 16 && d->cout != 32)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)d->cout, (cuuint64_t)(d->n * (int64_t)d->h * d->w)};
+  const cuuint64_t strides[1] = {(cuuint64_t)d->y_ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)d->cout, 128}, es[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             d->cout == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// residual of a 1x1 layer as {res_c channels, source pixels}: boxes {res_c, 64} (nearest-up2: the 64 source pixels under
+// 128 consecutive output pixels of one row) or {res_c, 128} (same resolution)
+static bool thin_tensor_map_r(const iea_conv_desc* d, CUtensorMap* tm) {
+  encode_tiled_fn enc = tma_encoder();
+  const bool up2 = d->res_mode == IEA_IN_UP2;
+  if (!enc || !d->res || d->res_dtype != IEA_BF16 || d->res_ld % 8 || ((uintptr_t)d->res & 15)) return false;
+  if ((d->res_c != 16 && d->res_c != 32) || d->res_c > d->cout) return false;
+  if (up2 && (d->w % 128 || d->h % 2)) return false;
+  if (!up2 && d->res_mode != IEA_IN_DIRECT) return false;
+  const int64_t px = up2 ? d->n * (int64_t)(d->h / 2) * (d->w / 2) : d->n * (int64_t)d->h * d->w;
+  const cuuint64_t dims[2] = {(cuuint64_t)d->res_c, (cuuint64_t)px};
+  const cuuint64_t strides[1] = {(cuuint64_t)d->res_ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)d->res_c, up2 ? 64u : 128u}, es[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->res), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             d->res_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // {8 channels, patch width, 18 rows, 1 image} boxes of the NHWC input for 3x3; {8 channels, 128 pixels} for 1x1
 static bool thin_tensor_map(const iea_conv_desc* d, bool is3, int mt, CUtensorMap* tm) {
   encode_tiled_fn enc = tma_encoder();
@@ -693,7 +792,7 @@ static bool thin_tensor_map(const iea_conv_desc* d, bool is3, int mt, CUtensorMa
 }
 
 template <int CPR, bool IS3, int MT, bool TMA>
-static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint32_t& smem) {
+static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint32_t& smem, bool tst = false) {
   using G = thin::Geo<CPR, IS3, MT, TMA>;
   p.d = *d;
   p.wtc = (const bf16*)d->wpack_tc;
@@ -720,12 +819,17 @@ static int thin_prepare(const iea_conv_desc* d, thin::Params& p, int& grid, uint
   p.stage_off = (p.w_bytes + 127) / 128 * 128;
   const uint32_t misc = (2 * cout_e + 2 * 4 * 2 * cout_e) * 4;  // scale, bias, statistics fold of both groups
   const uint32_t tail = misc + 512;
+  p.res_slot = tst ? (d->res_mode == IEA_IN_UP2 ? 64u : 128u) * (uint32_t)d->res_c * 2 : 0;
+  const uint32_t ring_bytes = tst ? 2 * thin::RES_RING * p.res_slot + 1024 : 0;
+  const uint32_t tst_bytes = tst ? 2 * 2 * 128 * 64 + 2048 + ring_bytes : 0;  // two groups x two sub-tile images (+ alignment)
   int stages = 8;  // even: the two producer groups own alternate ring slots
-  while (stages > 4 && p.stage_off + stages * G::STAGE + tail > 200 * 1024) stages -= 2;
+  while (stages > 4 && p.stage_off + stages * G::STAGE + tail + tst_bytes > 208 * 1024) stages -= 2;
   p.stages = stages;
   p.depth = stages >= 8 ? 3 : 2;  // items each group keeps in flight (it owns stages/2 slots)
   { const char* e_ = getenv("IEA_THIN_DEPTH"); if (e_ && atoi(e_) >= 2 && atoi(e_) <= stages / 2) p.depth = atoi(e_); }  // tuning aid
-  p.misc_off = p.stage_off + stages * G::STAGE;
+  p.tst_off = (p.stage_off + stages * G::STAGE + 1023) / 1024 * 1024;
+  p.res_off = p.tst_off + 2 * 2 * 128 * 64 + 1024;
+  p.misc_off = tst ? p.res_off + ring_bytes : p.stage_off + stages * G::STAGE;
   p.bar_off = (p.misc_off + misc + 15) / 16 * 16;
   smem = p.bar_off + 512;  // barriers: full, empty, landing (8 B x stages each), 2 x 4 accumulator, weights; TMEM slot
   uint32_t cols = 32;
@@ -750,20 +854,29 @@ static int thin_launch(const iea_conv_desc* d, cudaStream_t s, int* grid_only) {
   bool tma = TMA_OK && !grid_only && d->in_mode == IEA_IN_DIRECT && d->x_ld % 8 == 0;
   if (tma) { const char* e_ = getenv("IEA_THIN_TMA"); if (e_ && e_[0] == '0') tma = false; }
   if (tma) tma = thin_tensor_map(d, IS3, MT, &tm);
-  int rc = tma ? thin_prepare<CPR, IS3, MT, TMA_OK>(d, p, grid, smem) : thin_prepare<CPR, IS3, MT, false>(d, p, grid, smem);
+  // TMA store of the output: the residual flavour of the 1x1 layers, whole sub-tiles only (IEA_THIN_TST=0 disables)
+  alignas(64) CUtensorMap tmy;
+  memset(&tmy, 0, sizeof(tmy));
+  const bool simple = d->acc_c0 < 0 && d->act == IEA_ACT_NONE && d->cout != 1;
+  bool tst = !IS3 && tma && simple && d->res && d->res_mode != IEA_IN_POOL2 && (d->n * (int64_t)d->h * d->w) % (128 * MT) == 0;
+  if (tst) { const char* e_ = getenv("IEA_THIN_TST"); if (e_ && e_[0] == '0') tst = false; }
+  alignas(64) CUtensorMap tmr;
+  memset(&tmr, 0, sizeof(tmr));
+  if (tst) tst = thin_tensor_map_y(d, &tmy) && thin_tensor_map_r(d, &tmr);
+  int rc = tma ? thin_prepare<CPR, IS3, MT, TMA_OK>(d, p, grid, smem, tst) : thin_prepare<CPR, IS3, MT, false>(d, p, grid, smem);
   if (rc) return rc;
   if (grid_only) { *grid_only = grid; return 0; }
   auto run = [&](auto kern) -> int {
     IEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, thin::THREADS, smem, s>>>(p, tm);
+    kern<<<grid, thin::THREADS, smem, s>>>(p, tm, tmy, tmr);
     return check_launch("iea_conv_fprop(tcgen05 thin)");
   };
   // (a compile-time "plain" flavour measured no faster than the generic one -- without a residual the
   //  producers, not the epilogue, pace these kernels -- so only the residual flavour is specialised)
-  const bool simple = d->acc_c0 < 0 && d->act == IEA_ACT_NONE && d->cout != 1;
   if constexpr (TMA_OK) {
     if (tma) {
       if constexpr (!IS3) {
+        if (tst) return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 3, true>);
         if (simple && d->res && d->res_mode != IEA_IN_POOL2) return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 1, true>);
       }
       return run(thin::conv_thin_kernel<CPR, IS3, NB, MT, 2, true>);
