@@ -49,48 +49,48 @@ for src, dst in (("layers_train_full.txt", "layers_%s_train8.txt"), ("layers_sam
             f.write("# python tools/prof_layers.py: every C-ABI call of one step timed with CUDA events on the launching stream;\n"
                     "# GB/s = algorithmic bytes (input + output of the layer, bf16) / call time\n" + "\n".join(body[:140]) + "\n")
 
-rep = os.path.join(G, "prof_thin.ncu-rep")
-if os.path.exists(rep):
-    out = run("ncu", "-i", rep, "--page", "raw", "--csv")
-    rows = list(csv.reader(out.splitlines()))
-    h = rows[0]
-    keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size",
-            "launch__registers_per_thread", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
-            "smsp__average_warp_latency_per_inst_issued.ratio"]
-    picks = {"dominant": ("<2, 0, 2, 4, 1,", "16->32 1x1 @256x256 + up2 residual + stats, n=640"),
-             "best": ("<2, 1, 1, 4, 2,", "16->16 3x3 @256x256 (+BN/ReLU prologue, stats epilogue), n=640")}
-    found = {}
-    mul = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
+        "smsp__average_warp_latency_per_inst_issued.ratio"]
+what = {"l32_64": "32->64 1x1 @128x128 + ccbn/ReLU prologue + up2 residual + stats, n=640 (tc2::conv_tc2_kernel)",
+        "l32_1": "32->1 3x3 @256x256 + bn/ReLU prologue (output conv), n=640 (thin::conv_thin_kernel)",
+        "l16_32": "16->32 1x1 @256x256 + ccbn/ReLU prologue + up2 residual + stats, n=640 (thin::conv_thin_kernel, TMA-store flavour)",
+        "l16_16": "16->16 3x3 @256x256 + ccbn/ReLU prologue + stats, n=640 (thin::conv_thin_kernel)"}
+mul = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+found, text = {}, []
+for tag in ("l32_64", "l32_1", "l16_32", "l16_16"):
+    rep = os.path.join(G, "prof_%s.ncu-rep" % tag)
+    if not os.path.exists(rep):
+        continue
+    rows = list(csv.reader(run("ncu", "-i", rep, "--page", "raw", "--csv").splitlines()))
+    h, r = rows[0], rows[-1]
+    d = dict(zip(h, r))
+    text.append("\n[%s] %s\n%s" % (tag, what[tag], d["Kernel Name"]))
+    for k in keys:
+        if k in d:
+            text.append("  %-78s %s %s" % (k, d[k], rows[1][h.index(k)]))
+    rd = float(d["dram__bytes_read.sum"]) * mul[rows[1][h.index("dram__bytes_read.sum")]]
+    wr = float(d["dram__bytes_write.sum"]) * mul[rows[1][h.index("dram__bytes_write.sum")]]
+    found[tag] = {"kernel": what[tag], "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+                  "ncu_duration_us": float(d["gpu__time_duration.sum"]),
+                  "source": "profiles/ncu_top_kernel_%s.txt [%s] (dram__bytes_read.sum + dram__bytes_write.sum)" % (R, tag)}
+if found:
     with open(os.path.join(P, "ncu_top_kernel_%s.txt" % R), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:conv_thin_kernel -s 21 -c 2 : python tools/prof_sample.py 16 2\n"
-                "# the macro-tile tcgen05 conv launches of the second Generator forward (16 events = 640 images);\n"
-                "# template arguments <CPR, IS3, NB, MT, EPI, TMA>; bench.py's `roofline` (dominant launch by time) is the\n"
-                "# <2, 0, 2, 4, 1, 1> launch with the largest DRAM traffic, `roofline_best_kernel` the <2, 1, 1, 4, 2, 1> one\n")
-        for r in rows[2:]:
-            d = dict(zip(h, r))
-            f.write("\n%s\n" % d["Kernel Name"])
-            for k in keys:
-                if k in d:
-                    f.write("  %-70s %s %s\n" % (k, d[k], rows[1][h.index(k)]))
-            name = d["Kernel Name"].replace("(int)", "").replace("(bool)", "")
-            for key, (sig, what) in picks.items():
-                if "conv_thin_kernel" + sig in name:
-                    rd = float(d["dram__bytes_read.sum"]) * mul[rows[1][h.index("dram__bytes_read.sum")]]
-                    wr = float(d["dram__bytes_write.sum"]) * mul[rows[1][h.index("dram__bytes_write.sum")]]
-                    if key not in found or rd + wr > found[key]["dram_bytes_per_launch"]:
-                        found[key] = {"kernel": "thin::%s %s" % (name.replace("(Params, CUtensorMap_st)", ""), what),
-                                      "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
-                                      "ncu_duration_us": float(d["gpu__time_duration.sum"]), "launch_index": rows.index(r) - 2,
-                                      "source": "profiles/ncu_top_kernel_%s.txt (dram__bytes_read.sum + dram__bytes_write.sum)" % R}
-    if found:
-        with open(os.path.join(P, "top_kernel_traffic.json"), "w") as f:
-            json.dump(found, f, indent=1)
-            f.write("\n")
-    best = (0, 0, 0, found["dominant"]["launch_index"]) if "dominant" in found else None
-    st = run(sys.executable, "tools/ncu_stalls.py", rep, str(best[3] if best else 9), "30")
-    with open(os.path.join(P, "ncu_top_kernel_%s_stalls.txt" % R), "w") as f:
-        f.write("# python tools/ncu_stalls.py gpurun_out/prof_thin.ncu-rep <launch> 30 : warp-state samples per SASS line of the DOMINANT launch (16->32 1x1 + up2 residual)\n" + st)
+        f.write("# ncu --set full --clock-control none -k regex:conv_t -s 2 -c 1 : python tools/prof_kernel.py <tag> 3\n"
+                "# the four heaviest layers of a 16-event sampling pass (bench.py ROOFLINE_LAYERS), each launched alone on 640 images;\n"
+                "# the third (warm) launch is captured.  bench.py's `roofline` is the one with the longest live-measured launch.\n"
+                + "\n".join(text) + "\n")
+    with open(os.path.join(P, "top_kernel_traffic.json"), "w") as f:
+        json.dump(found, f, indent=1)
+        f.write("\n")
+    for tag in ("l32_64", "l16_32"):
+        rep = os.path.join(G, "prof_%s.ncu-rep" % tag)
+        if os.path.exists(rep):
+            st = run(sys.executable, "tools/ncu_stalls.py", rep, "0", "30")
+            with open(os.path.join(P, "ncu_top_kernel_%s_stalls_%s.txt" % (R, tag)), "w") as f:
+                f.write("# python tools/ncu_stalls.py gpurun_out/prof_%s.ncu-rep 0 30 : warp-state samples per SASS line, %s\n" % (tag, what[tag]) + st)
 print(sorted(os.listdir(P)))

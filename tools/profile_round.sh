@@ -3,8 +3,8 @@
 #   1. the plain bench lines (never under a profiler),
 #   2. per-call CUDA-event profiles of one train step / one sampling pass (tools/prof_layers.py),
 #   3. ncu launch lists (gpu__time_duration.sum) of two Generator sampling passes and of two train steps,
-#   4. `ncu --set full` captures of the dominant kernel of the sampling step (16->32 1x1 @256^2 + up2 residual,
-#      launch #... of conv_thin_kernel) and of the heaviest layer (16->16 3x3 @256^2).
+#   4. `ncu --set full` captures of the four heaviest layers of the sampling pass, each launched on its own
+#      (tools/prof_kernel.py: bench.py's ROOFLINE_LAYERS).
 set -u
 R=${1:-r02}
 O=gpurun_out
@@ -20,6 +20,13 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-fi
     python tools/prof_sample.py 16 2 > $O/ncu_sample.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $O/launches_train.csv \
     python tools/prof_train.py 8 2 > $O/ncu_train.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv_thin_kernel -s 21 -c 2 -f -o $O/prof_thin \
-    python tools/prof_sample.py 16 2 > $O/ncu_full.log 2>&1
+# the four heaviest layers of the sampling pass, each launched alone (third launch = warm): DRAM traffic, stalls
+for T in l32_64 l16_32; do
+  ncu --set full --clock-control none --import-source on -k regex:conv_t -s 2 -c 1 -f -o $O/prof_$T \
+      python tools/prof_kernel.py $T 3 > $O/ncu_$T.log 2>&1
+done
+for T in l32_1 l16_16; do
+  ncu --set full --clock-control none -k regex:conv_t -s 2 -c 1 -f -o $O/prof_$T \
+      python tools/prof_kernel.py $T 3 > $O/ncu_$T.log 2>&1
+done
 ls -la $O | tail -12

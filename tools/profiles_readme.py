@@ -37,9 +37,9 @@ L = ["# profiles/ -- measured evidence, round %s" % R[1:], "",
      "| `bench_%s_sample16_n2.json`, `_train8_n2.json`, `_train_strong64_n2.json` | the same lines under `torch.distributed.run --nproc-per-node 2` (weak scaling) and 64 events over 2 GPUs (strong scaling, 8-event micro-batches) |" % R,
      "| `layers_%s_{train8,sample16}.txt` | every C-ABI call of one step timed with CUDA events, grouped by (entry point, shape), algorithmic GB/s per conv (`tools/prof_layers.py`) |" % R,
      "| `launches_%s_{train8,sample16}.txt` | ncu `gpu__time_duration.sum` launch lists, summed per kernel (`tools/launch_summary.py`) |" % R,
-     "| `ncu_top_kernel_%s.txt` | `ncu --set full` of the dominant launch of the sampling step (16->32 1x1 @256^2 + up2 residual) and of the 16->16 3x3 @256^2 launch, 640 images |" % R,
-     "| `ncu_top_kernel_%s_stalls.txt` | warp-state samples per SASS line of the dominant launch (`tools/ncu_stalls.py`) |" % R,
-     "| `top_kernel_traffic.json` | DRAM bytes of those two launches (read by `bench.py` for `roofline.traffic`) |",
+     "| `ncu_top_kernel_%s.txt` | `ncu --set full` of the four heaviest layers of the sampling pass, each launched alone on 640 images (`tools/prof_kernel.py`: 32->64 1x1 @128^2 + up2 residual, 32->1 3x3 @256^2, 16->32 1x1 @256^2 + up2 residual, 16->16 3x3 @256^2) |" % R,
+     "| `ncu_top_kernel_%s_stalls_l32_64.txt`, `_stalls_l16_32.txt` | warp-state samples per SASS line of the longest launch and of round 1's dominant launch (`tools/ncu_stalls.py`) |" % R,
+     "| `top_kernel_traffic.json` | DRAM bytes of those four launches (read by `bench.py` for `roofline.traffic`) |",
      "| `ncu_attention_r01.txt` | `ncu --set full` of the tcgen05 / TMEM self-attention kernels (unchanged since round 1) |", ""]
 if b:
     ts = tg or b.get("train_step")
@@ -64,12 +64,13 @@ if b:
     if b.get("hbase3"):
         L += ["| G sampling at the shipped geometry 256x768 (H_base = 3), 8 events | %.1f events/s (%.1f ms/step), %.1f %% of the HBM roofline |" % (
             b["hbase3"]["value"], b["hbase3"]["ms_per_step"], 100 * b["hbase3"]["step_roofline"]["frac_of_hbm_peak"])]
-    for key, what in (("roofline", "DOMINANT launch of the sampling step"), ("roofline_best_kernel", "best launch")):
+    for key, what in (("roofline", "LONGEST launch of the sampling step (chosen live)"),
+                      ("roofline_r1_dominant", "round 1's dominant launch (0.30 then)"), ("roofline_best_kernel", "best launch")):
         r = b.get(key)
         if r and "achieved" in r:
             tr = r.get("traffic")
             L += ["| %s: %s | %.3f ms, %.0f GB/s algorithmic = **%.1f %% of HBM peak**; DRAM traffic %s vs %.2f GB algorithmic%s |" % (
-                what, r["kernel"].split(" (thin")[0].replace("iea_conv_fprop ", ""), r["ms_per_launch"], r["achieved"], 100 * r["frac"],
+                what, r["kernel"].split(" (thin")[0].split(" (tc2")[0].replace("iea_conv_fprop ", ""), r["ms_per_launch"], r["achieved"], 100 * r["frac"],
                 ("%.2f GB (%.0f GB/s = %.1f %% of peak)" % (tr / 1e9, tr / r["ms_per_launch"] / 1e6, tr / r["ms_per_launch"] / 1e6 / r["peak"] * 100)) if tr else "n/a",
                 r["algorithmic_bytes_per_launch"] / 1e9,
                 (" (+%.2f GB fused residual read, not counted)" % (r["fused_extra_bytes"] / 1e9)) if r.get("fused_extra_bytes") else "")]
