@@ -29,4 +29,9 @@ for T in l32_1 l16_16; do
   ncu --set full --clock-control none -k regex:conv_t -s 2 -c 1 -f -o $O/prof_$T \
       python tools/prof_kernel.py $T 3 > $O/ncu_$T.log 2>&1
 done
+# summaries are made HERE (the .ncu-rep files together exceed what gpurun copies back) and travel as text
+python tools/make_profiles.py $R > $O/make_profiles.log 2>&1
+python tools/profiles_readme.py $R >> $O/make_profiles.log 2>&1
+rm -rf $O/profiles_new && cp -r profiles $O/profiles_new
+rm -f $O/*.ncu-rep
 ls -la $O | tail -12
