@@ -985,7 +985,10 @@ static int tc2_prepare(const iea_conv_desc* d, tc2::Params& p, int& grid, uint32
   p.fd_tw = tc2::make_fastdiv(p.tiles_w); p.fd_th = tc2::make_fastdiv(p.tiles_h);
   p.npix = is3 ? tc2::PH * tc2::PW : 128;
   const int cpr = p.KB / 8;
-  p.plane = (p.npix * 16 + 127) / 128 * 128 + (cpr == 8 ? 64 : 0);
+  // planes (8 channels each) are skewed by 128 / CPR bytes: the CPR chunks of a pixel are copied / transformed by
+  // consecutive threads and must fall into different banks (ncu, 32 -> 64 1x1 @128^2 with unskewed planes: 122 M
+  // shared-memory bank conflicts, L1 data pipe 76 % busy)
+  p.plane = (p.npix * 16 + 127) / 128 * 128 + 128 / cpr;
   p.stage_bytes = (cpr * p.plane + 127) / 128 * 128;
   p.w_bytes = (uint32_t)((int64_t)p.BN * cin_eff * p.taps * 2);
   p.stage_off = (p.w_bytes + 127) / 128 * 128;

@@ -87,10 +87,12 @@ if found:
     with open(os.path.join(P, "top_kernel_traffic.json"), "w") as f:
         json.dump(found, f, indent=1)
         f.write("\n")
-    for tag in ("l32_64", "l16_32"):
+    for tag in ("l32_64", "l32_1", "l16_32", "l16_16"):
         rep = os.path.join(G, "prof_%s.ncu-rep" % tag)
         if os.path.exists(rep):
             st = run(sys.executable, "tools/ncu_stalls.py", rep, "0", "30")
+            ro = run(sys.executable, "tools/dbg/ncu_roles.py", rep, "0")
             with open(os.path.join(P, "ncu_top_kernel_%s_stalls_%s.txt" % (R, tag)), "w") as f:
-                f.write("# python tools/ncu_stalls.py gpurun_out/prof_%s.ncu-rep 0 30 : warp-state samples per SASS line, %s\n" % (tag, what[tag]) + st)
+                f.write("# python tools/ncu_stalls.py gpurun_out/prof_%s.ncu-rep 0 30 : warp-state samples per SASS line, %s\n" % (tag, what[tag]) + st
+                        + "\n# python tools/dbg/ncu_roles.py: samples / instructions between the synchronisation sites, in SASS order (the warp roles)\n" + ro)
 print(sorted(os.listdir(P)))

@@ -21,12 +21,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $O/launches_train.csv \
     python tools/prof_train.py 8 2 > $O/ncu_train.log 2>&1
 # the four heaviest layers of the sampling pass, each launched alone (third launch = warm): DRAM traffic, stalls
-for T in l32_64 l16_32; do
+for T in l32_64 l32_1 l16_32 l16_16; do
   ncu --set full --clock-control none --import-source on -k regex:conv_t -s 2 -c 1 -f -o $O/prof_$T \
-      python tools/prof_kernel.py $T 3 > $O/ncu_$T.log 2>&1
-done
-for T in l32_1 l16_16; do
-  ncu --set full --clock-control none -k regex:conv_t -s 2 -c 1 -f -o $O/prof_$T \
       python tools/prof_kernel.py $T 3 > $O/ncu_$T.log 2>&1
 done
 # summaries are made HERE (the .ncu-rep files together exceed what gpurun copies back) and travel as text
