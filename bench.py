@@ -241,7 +241,7 @@ def kernel_rooflines(E_, hbm_peak, which):
         ms = _time_call(call)
         ach = bytes_ / (ms * 1e-3) / 1e9
         t = traffic.get(tag, {})
-        res[tag] = {"bound": "hbm", "kernel": label, "achieved": round(ach, 1), "peak": hbm_peak, "peak_source": which,
+        res[tag] = {"bound": "hbm", "tag": tag, "kernel": label, "achieved": round(ach, 1), "peak": hbm_peak, "peak_source": which,
                     "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": t.get("dram_bytes_per_launch"),
                     "traffic_source": t.get("source"), "ms_per_launch": round(ms, 4),
                     "algorithmic_bytes_per_launch": bytes_, "fused_extra_bytes": extra, "images": 640}

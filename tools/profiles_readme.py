@@ -39,6 +39,8 @@ L = ["# profiles/ -- measured evidence, round %s" % R[1:], "",
      "| `launches_%s_{train8,sample16}.txt` | ncu `gpu__time_duration.sum` launch lists, summed per kernel (`tools/launch_summary.py`) |" % R,
      "| `ncu_top_kernel_%s.txt` | `ncu --set full` of the four heaviest layers of the sampling pass, each launched alone on 640 images (`tools/prof_kernel.py`: 32->64 1x1 @128^2 + up2 residual, 32->1 3x3 @256^2, 16->32 1x1 @256^2 + up2 residual, 16->16 3x3 @256^2) |" % R,
      "| `ncu_top_kernel_%s_stalls_l32_64.txt`, `_stalls_l16_32.txt` | warp-state samples per SASS line of the longest launch and of round 1's dominant launch (`tools/ncu_stalls.py`) |" % R,
+     "| `ncu_top_kernel_%s_stalls_l32_1.txt`, `_stalls_l16_16.txt` | the same for the output conv (longest launch at the end of the round) and the 3x3 layer; each file ends with the per-role view of `tools/dbg/ncu_roles.py` |" % R,
+     "| `ncu_top_kernel_%s_stalls_l16_32_before_tma.txt` | the 16->32 layer BEFORE its epilogue moved to TMA (1.82 ms: 45 %% of the epilogue's samples on per-pixel residual loads) |" % R,
      "| `top_kernel_traffic.json` | DRAM bytes of those four launches (read by `bench.py` for `roofline.traffic`) |",
      "| `ncu_attention_r01.txt` | `ncu --set full` of the tcgen05 / TMEM self-attention kernels (unchanged since round 1) |", ""]
 if b:
@@ -69,6 +71,14 @@ if b:
         r = b.get(key)
         if r and "achieved" in r:
             tr = r.get("traffic")
+            if not tr:  # (a bench line written before the capture of the same round: take the committed capture)
+                tj = os.path.join(P, "top_kernel_traffic.json")
+                if os.path.exists(tj):
+                    with open(tj) as f:
+                        tt = json.load(f)
+                    for sub, tag in (("32->1 3x3", "l32_1"), ("32->64 1x1", "l32_64"), ("16->32 1x1", "l16_32"), ("16->16 3x3", "l16_16")):
+                        if sub in r["kernel"] and tag in tt:
+                            tr = tt[tag]["dram_bytes_per_launch"]
             L += ["| %s: %s | %.3f ms, %.0f GB/s algorithmic = **%.1f %% of HBM peak**; DRAM traffic %s vs %.2f GB algorithmic%s |" % (
                 what, r["kernel"].split(" (thin")[0].split(" (tc2")[0].replace("iea_conv_fprop ", ""), r["ms_per_launch"], r["achieved"], 100 * r["frac"],
                 ("%.2f GB (%.0f GB/s = %.1f %% of peak)" % (tr / 1e9, tr / r["ms_per_launch"] / 1e6, tr / r["ms_per_launch"] / 1e6 / r["peak"] * 100)) if tr else "n/a",
