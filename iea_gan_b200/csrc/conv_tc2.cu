@@ -724,7 +724,23 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
             const int64_t left = p.M - o.m0 - r0;  // rows of this tile that exist, from r0 on
             if (left < (int64_t)(cg - 1) * step + 1) rows_left = left <= 0 ? 0 : (int)((left - 1) / step) + 1;
           }
-          for (int it = 0; it < rows_left; ++it) {
+          int it = 0;
+          for (; it + 4 <= rows_left; it += 4) {  // four rows per pass: the shared-memory reads are issued back to back
+            uint4 v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v4[u] = *reinterpret_cast<const uint4*>(sp + u * sstep);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              *reinterpret_cast<uint4*>(yp + u * ystep) = v4[u];
+              if (STATS) {
+                const uint32_t w[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = bf2_to_f2(w[j]); s1[j] = fadd2(s1[j], f); s2[j] = ffma2(f, f, s2[j]); }
+              }
+            }
+            sp += 4 * sstep; yp += 4 * ystep;
+          }
+          for (; it < rows_left; ++it) {
             const uint4 v4 = *reinterpret_cast<const uint4*>(sp);
             *reinterpret_cast<uint4*>(yp) = v4;
             if (STATS) {
@@ -736,11 +752,10 @@ __global__ void __launch_bounds__(THREADS, OCC) conv_tc2_kernel(const Params p) 
           }
         }
         if (STATS) {  // [part = r0][BN][2] partials, then a fixed-order fold over the parts
+          // (16-byte stores: the scalar version was a 16-way bank conflict -- the r0 rows of partials are 2 BN floats apart)
+          float4* st4 = reinterpret_cast<float4*>(stat + (r0 * p.BN + g8 * 8) * 2);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            stat[(r0 * p.BN + g8 * 8 + 2 * j) * 2] = s1[j].x; stat[(r0 * p.BN + g8 * 8 + 2 * j) * 2 + 1] = s2[j].x;
-            stat[(r0 * p.BN + g8 * 8 + 2 * j + 1) * 2] = s1[j].y; stat[(r0 * p.BN + g8 * 8 + 2 * j + 1) * 2 + 1] = s2[j].y;
-          }
+          for (int j = 0; j < 4; ++j) st4[j] = make_float4(s1[j].x, s2[j].x, s1[j].y, s2[j].y);
           bar_sync_epi();
           for (int c = et; c < p.BN * 2; c += 128) {
             float a = 0.f;
