@@ -97,6 +97,7 @@ _SIG = {
     "iea_embedding_bwd": [vp, vp, vp, i64, i32, i32, vp, vp],
     "iea_relu_sumpool_fwd": [vp, i32, i64, i64, i32, vp, vp],
     "iea_relu_sumpool_bwd": [vp, i32, vp, i64, i64, i32, vp, i32, vp],
+    "iea_avgpool2_fwd": [vp, i32, i64, i32, i32, i32, i32, vp, i32, vp],
     "iea_maxpool2_fwd": [vp, i32, i64, i32, i32, i32, vp, vp, vp],
     "iea_maxpool2_bwd": [vp, i32, vp, i64, i32, i32, i32, vp, vp],
     "iea_layernorm_fwd": [vp, vp, vp, i64, i32, f32, vp, vp, vp, vp],

@@ -179,6 +179,40 @@ __global__ void relu_sumpool_bwd_kernel(const void* x, int dt, const float* dout
   }
 }
 
+// ---- 2x2 average pool (the DBlock shortcut: model.py:541-557 pools x once for both conv_sc and the identity half) ----
+// one thread per (output pixel, 16-byte chunk): vector loads of the four source pixels, fp32 average
+template <typename T, int V>
+__global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const T* x, int64_t n, int h, int w, int c, int x_ld, T* y, int y_ld) {
+  const int ho = h / 2, wo = w / 2, cv = c / V;
+  const int64_t total = n * ho * (int64_t)wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % cv) * V;
+    const int64_t pix = i / cv;
+    const int xo = (int)(pix % wo);
+    const int64_t t = pix / wo;
+    const int yo = (int)(t % ho);
+    const int64_t nn = t / ho;
+    const T* s0 = x + ((nn * h + 2 * yo) * (int64_t)w + 2 * xo) * x_ld + cc;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const uint4 q = *reinterpret_cast<const uint4*>(s0 + ((int64_t)a * w + b) * x_ld);
+        const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += (float)e[j];
+      }
+    uint4 o;
+    T* eo = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int j = 0; j < V; ++j) eo[j] = (T)(0.25f * acc[j]);
+    *reinterpret_cast<uint4*>(y + pix * y_ld + cc) = o;
+  }
+}
+
 // ---- 2x2 max pool ----
 __global__ void maxpool2_fwd_kernel(const void* x, int dt, int64_t n, int h, int w, int c, void* y, uint8_t* idx) {
   const int ho = h / 2, wo = w / 2;
@@ -476,6 +510,18 @@ int iea_relu_sumpool_bwd(const void* x, int dt, const float* dout, int64_t n, in
                          iea_stream_t st) {
   relu_sumpool_bwd_kernel<<<ew_blocks(n * hw * c), 256, 0, (cudaStream_t)st>>>(x, dt, dout, n, hw, c, dx, ddt);
   return check_launch("iea_relu_sumpool_bwd");
+}
+int iea_avgpool2_fwd(const void* x, int dt, int64_t n, int h, int w, int c, int x_ld, void* y, int y_ld, iea_stream_t st) {
+  IEA_CHECK_ARG(h % 2 == 0 && w % 2 == 0, "iea_avgpool2_fwd: odd spatial size %dx%d", h, w);
+  const int v = dt == IEA_BF16 ? 8 : 4;
+  IEA_CHECK_ARG(c % v == 0 && x_ld % v == 0 && y_ld % v == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                "iea_avgpool2_fwd: channel counts / pitches must be multiples of %d elements and 16-byte aligned", v);
+  const int64_t total = n * (h / 2) * (int64_t)(w / 2) * (c / v);
+  if (dt == IEA_BF16)
+    avgpool2_fwd_kernel<bf16, 8><<<ew_blocks(total), 256, 0, (cudaStream_t)st>>>((const bf16*)x, n, h, w, c, x_ld, (bf16*)y, y_ld);
+  else
+    avgpool2_fwd_kernel<float, 4><<<ew_blocks(total), 256, 0, (cudaStream_t)st>>>((const float*)x, n, h, w, c, x_ld, (float*)y, y_ld);
+  return check_launch("iea_avgpool2_fwd");
 }
 int iea_maxpool2_fwd(const void* x, int dt, int64_t n, int h, int w, int c, void* y, uint8_t* idx, iea_stream_t st) {
   IEA_CHECK_ARG(h % 2 == 0 && w % 2 == 0, "iea_maxpool2_fwd: odd spatial size %dx%d", h, w);

@@ -1132,6 +1132,22 @@ def adu_postprocess(img):
 
 
 # ------------------------------------------------------------------ Discriminator ops
+def avgpool2_into(tape, xv, out, n, hh, ww):
+    """nn.AvgPool2d(2) of xv (n x hh x ww) written into the channel window `out` of a (n x hh/2 x ww/2) tensor.
+    Backward: the un-pooling adjoint of out's gradient, accumulated onto xv's (iea_residual_bwd, POOL2 mode)."""
+    c = xv.c
+    K("iea_avgpool2_fwd", xv.off(), dt(xv.t), n, hh, ww, c, xv.ld, out.off(), out.ld, L.stream())
+    if tape.record and xv.need:
+        def bw():
+            if out.g is None:
+                return
+            rg, beta = _accum_target(xv)
+            K("iea_residual_bwd", out.off(out.g), dt(out.g), out.ld, n, hh // 2, ww // 2, c, L.IN_POOL2, xv.off(rg), dt(rg),
+              xv.ld, xv.c, beta, L.stream())
+        tape.add(bw)
+    return out
+
+
 def maxpool2(tape, xv, n, hh, ww):
     c = xv.c
     y = torch.empty((n, hh // 2, ww // 2, c), dtype=xv.t.dtype, device=xv.t.device)
@@ -1259,6 +1275,27 @@ def _dblock(tape, blk, x, n, hh, ww, h_):
     h3 = conv(tape, h2, h_[blk.conv3], n, hh, ww, 3, bias=blk.conv3.bias, in_relu=True)
     ho, wo = (hh // 2, ww // 2) if down else (hh, ww)
     mode = L.IN_POOL2 if down else L.IN_DIRECT
+    if down and blk.learnable_sc and _env(b"IEA_DBLOCK_POOL_ONCE", "IEA_DBLOCK_POOL_ONCE", "0") == "1":
+        # OPT-IN (IEA_DBLOCK_POOL_ONCE=1): the shortcut torch.cat([pool(x), conv_sc(pool(x))], 1) as ONE tensor R.  x is
+        # pooled once into R[..., :cin] (by default it is gathered 2x2 twice, by conv_sc's prologue and by conv4's residual
+        # read), conv_sc reads that window at the low resolution and writes R[..., cin:], conv4 takes R as a plain
+        # same-resolution residual (its fast epilogue), and the backward un-pools once.  148.0 -> 142.8 ms per 8-event
+        # train step and exact with fp32 activations (tests/test_gpu_discriminator.py) -- but with bf16 activations the
+        # identity half is rounded BEFORE the add, and the attention theta / phi gradients of the full-size net (the most
+        # rounding-sensitive tensors of D at random init) move from 12-15 % to 39-42 % off the fp32 oracle, everything
+        # else unchanged (tools/dbg/d_parity.py).  Not the default for that reason.
+        R = Var(torch.empty((n, ho, wo, cout), dtype=act_dtype(), device=x.t.device))
+        xp, scv = Var(R.t, c0=0, c=cin), Var(R.t, c0=cin, c=cout - cin)
+        avgpool2_into(tape, x, xp, n, hh, ww)
+        conv(tape, xp, h_[blk.conv_sc], n, ho, wo, 1, bias=blk.conv_sc.bias, out=scv)
+        if tape.record:
+            def link():  # conv4's backward has produced R's gradient: both windows read / extend it
+                xp.g = R.g
+                scv.g = R.g
+            tape.add(link)
+        y = conv(tape, h3, h_[blk.conv4], n, ho, wo, 1, bias=blk.conv4.bias, in_relu=True, in_mode=mode, res=R,
+                 res_mode=L.IN_DIRECT, res_c=cout)
+        return y, ho, wo
     y = Var(torch.empty((n, ho, wo, cout), dtype=act_dtype(), device=x.t.device))
     if blk.learnable_sc:
         scv = Var(y.t, c0=cin, c=cout - cin)

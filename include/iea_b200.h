@@ -290,6 +290,12 @@ int iea_relu_sumpool_fwd(const void* x, int x_dtype, int64_t n, int64_t hw, int 
                          iea_stream_t stream);
 int iea_relu_sumpool_bwd(const void* x, int x_dtype, const float* dout, int64_t n, int64_t hw, int c,
                          void* dx, int dx_dtype, iea_stream_t stream);
+/* nn.AvgPool2d(2) of an NHWC tensor (channel windows: x_ld / y_ld are the row pitches in elements): the DBlock
+ * shortcut pools its input once, model.py:541-557 (`downsample(x)` feeds both conv_sc and the identity half).
+ * The adjoint is iea_residual_bwd with res_mode = IEA_IN_POOL2. */
+int iea_avgpool2_fwd(const void* x, int dtype, int64_t n, int h, int w, int c, int x_ld, void* y, int y_ld,
+                     iea_stream_t stream);
+
 /* F.max_pool2d(x, 2): layers.py:286-287 (index saved as uint8 0..3) */
 int iea_maxpool2_fwd(const void* x, int dtype, int64_t n, int h, int w, int c, void* y, uint8_t* idx,
                      iea_stream_t stream);

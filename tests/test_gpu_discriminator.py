@@ -219,3 +219,14 @@ def test_full_size_discriminator_forward_backward_vs_oracle(adt, t_out, t_w, t_d
     assert rel(xg.grad, xr.grad) < t_dx
     for n in names:
         assert rel(got[n], sd[n].grad) < t_w, n
+
+
+def test_full_size_discriminator_pooled_once_shortcut_fp32():
+    """The opt-in DBlock shortcut that pools x once (IEA_DBLOCK_POOL_ONCE=1: iea_avgpool2_fwd, conv_sc on the low
+    resolution window, conv4 with a plain residual, one un-pooling adjoint) is the same function: with fp32 activations
+    it meets the tolerances of the default path against the CPU oracle."""
+    os.environ["IEA_DBLOCK_POOL_ONCE"] = "1"
+    try:
+        test_full_size_discriminator_forward_backward_vs_oracle("fp32", 1e-5, 1e-3, 1e-2)
+    finally:
+        os.environ.pop("IEA_DBLOCK_POOL_ONCE", None)
