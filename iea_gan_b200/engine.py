@@ -1282,7 +1282,7 @@ def _dblock(tape, blk, x, n, hh, ww, h_):
         # same-resolution residual (its fast epilogue), and the backward un-pools once.  148.0 -> 142.8 ms per 8-event
         # train step and exact with fp32 activations (tests/test_gpu_discriminator.py) -- but with bf16 activations the
         # identity half is rounded BEFORE the add, and the attention theta / phi gradients of the full-size net (the most
-        # rounding-sensitive tensors of D at random init) move from 12-15 % to 39-42 % off the fp32 oracle, everything
+        # rounding-sensitive tensors of D at random init) move from 12-15 % to 39-42 % off the fp32 CPU restatement, everything
         # else unchanged (tools/dbg/d_parity.py).  Not the default for that reason.
         R = Var(torch.empty((n, ho, wo, cout), dtype=act_dtype(), device=x.t.device))
         xp, scv = Var(R.t, c0=0, c=cin), Var(R.t, c0=cin, c=cout - cin)
