@@ -21,7 +21,8 @@ for src, dst in (("bench_%s.json" % R, "bench_%s_sample16.json"), ("bench_%s_tra
                  ("bench_%s_train_eager.json" % R, "bench_%s_train8_eager.json"), ("bench_%s_train1.json" % R, "bench_%s_train1_graph.json"),
                  ("bench_%s_sweep.json" % R, "bench_%s_attn_sweep.json"), ("bench_%s_ref.json" % R, "bench_%s_reference_arm.json"),
                  ("bench_%s_n2.json" % R, "bench_%s_sample16_n2.json"), ("bench_%s_train_n2.json" % R, "bench_%s_train8_n2.json"),
-                 ("bench_%s_strong64_n2.json" % R, "bench_%s_train_strong64_n2.json")):
+                 ("bench_%s_strong64_n2.json" % R, "bench_%s_train_strong64_n2.json"),
+                 ("bench_%s_n4.json" % R, "bench_%s_sample16_n4.json"), ("bench_%s_train_n4.json" % R, "bench_%s_train8_n4.json")):
     p = os.path.join(G, src)
     if os.path.exists(p):
         with open(os.path.join(P, dst % R), "w") as f:

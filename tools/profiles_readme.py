@@ -24,6 +24,7 @@ def g(d, *ks, default=None):
 b, tg, te, t1, sw, ref = (load("bench_%s_%s.json" % (R, k)) for k in (
     "sample16", "train8_graph", "train8_eager", "train1_graph", "attn_sweep", "reference_arm"))
 n2s, n2t, n2strong = (load("bench_%s_%s.json" % (R, k)) for k in ("sample16_n2", "train8_n2", "train_strong64_n2"))
+n4s, n4t = (load("bench_%s_%s.json" % (R, k)) for k in ("sample16_n4", "train8_n4"))
 L = ["# profiles/ -- measured evidence, round %s" % R[1:], "",
      "Everything here comes from one B200 box per call through `gpurun`; raw outputs land in `gpurun_out/` (scratch) and",
      "`tools/profile_round.sh` -> `tools/make_profiles.py` -> `tools/profiles_readme.py` turn them into these tracked files.",
@@ -34,7 +35,7 @@ L = ["# profiles/ -- measured evidence, round %s" % R[1:], "",
      "| `bench_%s_train8_graph.json`, `_train8_eager.json`, `_train1_graph.json` | `--workload train`: the full G+D step, 8 events as a CUDA graph / launched kernel by kernel, and 1 event as a graph |" % R,
      "| `bench_%s_attn_sweep.json` | `--workload attn-sweep` (BASELINE configs[4]): both RRMs and the self-attention block over 1..256 events, fwd and fwd+bwd |" % R,
      "| `bench_%s_reference_arm.json` | `--impl reference`: the UNMODIFIED reference (baseline/_ref) on the box's host cores: `model.generate` and the `train_fns` G+D step |" % R,
-     "| `bench_%s_sample16_n2.json`, `_train8_n2.json`, `_train_strong64_n2.json` | the same lines under `torch.distributed.run --nproc-per-node 2` (weak scaling) and 64 events over 2 GPUs (strong scaling, 8-event micro-batches) |" % R,
+     "| `bench_%s_sample16_n2.json`, `_train8_n2.json`, `_train_strong64_n2.json`, `_sample16_n4.json`, `_train8_n4.json` | the same lines under `torch.distributed.run --nproc-per-node 2 / 4` (weak scaling) and 64 events over 2 GPUs (strong scaling, 8-event micro-batches) |" % R,
      "| `layers_%s_{train8,sample16}.txt` | every C-ABI call of one step timed with CUDA events, grouped by (entry point, shape), algorithmic GB/s per conv (`tools/prof_layers.py`) |" % R,
      "| `launches_%s_{train8,sample16}.txt` | ncu `gpu__time_duration.sum` launch lists, summed per kernel (`tools/launch_summary.py`) |" % R,
      "| `ncu_top_kernel_%s.txt` | `ncu --set full` of the four heaviest layers of the sampling pass, each launched alone on 640 images (`tools/prof_kernel.py`: 32->64 1x1 @128^2 + up2 residual, 32->1 3x3 @256^2, 16->32 1x1 @256^2 + up2 residual, 16->16 3x3 @256^2) |" % R,
@@ -100,6 +101,10 @@ if b:
         L += ["| 2 GPUs, weak scaling: train step 8 events/GPU, flat-buffer NCCL all-reduce inside the captured graph | %.2f events/s (%.1f ms/step) |" % (n2t["value"], n2t["ms_per_step"])]
     if n2strong:
         L += ["| 2 GPUs, strong scaling (BASELINE configs[3]): 64 events per step, 32 per GPU in 8-event micro-batches | %.2f events/s (%.1f ms/step) |" % (n2strong["value"], n2strong["ms_per_step"])]
+    if n4s:
+        L += ["| 4 GPUs, weak scaling: sampling 16 events/GPU | %.1f events/s |" % n4s["value"]]
+    if n4t:
+        L += ["| 4 GPUs, weak scaling: train step 8 events/GPU | %.2f events/s (%.1f ms/step) |" % (n4t["value"], n4t["ms_per_step"])]
     if sw:
         L += ["", "## RRM + self-attention sweep (BASELINE configs[4], `bench_%s_attn_sweep.json`)" % R, "",
               "| op | events | fwd ms | fwd+bwd ms | fwd TFLOP/s | fwd frac of bf16 tensor peak |", "|---|---|---|---|---|---|"]
