@@ -517,3 +517,22 @@ def test_fused_1x1_backward_vs_torch(eng, cin, cout, hw, relu, aff, ds, resm, be
         assert L.call("iea_conv_bwd1x1_grid", C.byref(dq)) > 0
     finally:
         os.environ.pop("IEA_ACT_DTYPE", None)
+
+
+@pytest.mark.parametrize("dtype,c,ld_in,ld_out", [(torch.bfloat16, 32, 32, 64), (torch.float32, 16, 24, 16), (torch.bfloat16, 64, 64, 64)])
+def test_avgpool2_channel_windows_vs_torch(eng, dtype, c, ld_in, ld_out):
+    """iea_avgpool2_fwd (nn.AvgPool2d(2) of an NHWC channel window into a channel window, model.py:541-557) against
+    torch: fp32 average of the four pixels, one rounding to the storage dtype; untouched channels stay untouched."""
+    from iea_gan_b200 import _lib as L
+    torch.manual_seed(4)
+    n, h, w = 3, 12, 20
+    x = torch.randn(n, h, w, ld_in, device="cuda").to(dtype)
+    y = torch.full((n, h // 2, w // 2, ld_out), 7.0, device="cuda").to(dtype)
+    L.call("iea_avgpool2_fwd", x.data_ptr(), L.dt(x), n, h, w, c, ld_in, y.data_ptr(), ld_out, L.stream())
+    ref = torch.nn.functional.avg_pool2d(x[..., :c].float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).to(dtype)
+    torch.cuda.synchronize()
+    if dtype == torch.bfloat16:
+        assert torch.equal(y[..., :c], ref)  # sums of four bf16 values are exact in fp32
+    else:
+        assert torch.allclose(y[..., :c], ref, rtol=1e-6, atol=1e-7)
+    assert bool((y[..., c:] == 7.0).all())
