@@ -31,7 +31,7 @@ L = ["# profiles/ -- measured evidence, round %s" % R[1:], "",
      "Bench numbers are never taken under a profiler; ncu launch times are cold-cache and serialised (compare shares, not",
      "absolutes).  Round-1 files (`*_r01_*`) are kept for comparison.", "",
      "| File | What |", "|---|---|",
-     "| `bench_%s_sample16.json` | default `python bench.py` line: Generator sampling, 16 events, + `train_step` (graph, 20 steps, per-step spread, CPU baseline) / `hbase3` / `roofline` (dominant launch) / `roofline_best_kernel` / `stock_torch_gpu` / `cpu_baseline` |" % R,
+     "| `bench_%s_sample16.json` | default `python bench.py` line: Generator sampling, 16 events, + `train_step` (graph, 20 steps, per-step spread, CPU baseline) / `hbase3` / `roofline` (longest launch, chosen live) / `roofline_r1_dominant` / `roofline_best_kernel` / `stock_torch_gpu` / `cpu_baseline` |" % R,
      "| `bench_%s_train8_graph.json`, `_train8_eager.json`, `_train1_graph.json` | `--workload train`: the full G+D step, 8 events as a CUDA graph / launched kernel by kernel, and 1 event as a graph |" % R,
      "| `bench_%s_attn_sweep.json` | `--workload attn-sweep` (BASELINE configs[4]): both RRMs and the self-attention block over 1..256 events, fwd and fwd+bwd |" % R,
      "| `bench_%s_reference_arm.json` | `--impl reference`: the UNMODIFIED reference (baseline/_ref) on the box's host cores: `model.generate` and the `train_fns` G+D step |" % R,
@@ -39,7 +39,7 @@ L = ["# profiles/ -- measured evidence, round %s" % R[1:], "",
      "| `layers_%s_{train8,sample16}.txt` | every C-ABI call of one step timed with CUDA events, grouped by (entry point, shape), algorithmic GB/s per conv (`tools/prof_layers.py`) |" % R,
      "| `launches_%s_{train8,sample16}.txt` | ncu `gpu__time_duration.sum` launch lists, summed per kernel (`tools/launch_summary.py`) |" % R,
      "| `ncu_top_kernel_%s.txt` | `ncu --set full` of the four heaviest layers of the sampling pass, each launched alone on 640 images (`tools/prof_kernel.py`: 32->64 1x1 @128^2 + up2 residual, 32->1 3x3 @256^2, 16->32 1x1 @256^2 + up2 residual, 16->16 3x3 @256^2) |" % R,
-     "| `ncu_top_kernel_%s_stalls_l32_64.txt`, `_stalls_l16_32.txt` | warp-state samples per SASS line of the longest launch and of round 1's dominant launch (`tools/ncu_stalls.py`) |" % R,
+     "| `ncu_top_kernel_%s_stalls_l32_64.txt`, `_stalls_l16_32.txt` | warp-state samples per SASS line of the heaviest `conv_tc2` launch and of round 1's dominant launch (`tools/ncu_stalls.py`) |" % R,
      "| `ncu_top_kernel_%s_stalls_l32_1.txt`, `_stalls_l16_16.txt` | the same for the output conv (longest launch at the end of the round) and the 3x3 layer; each file ends with the per-role view of `tools/dbg/ncu_roles.py` |" % R,
      "| `ncu_top_kernel_%s_stalls_l16_32_before_tma.txt` | the 16->32 layer BEFORE its epilogue moved to TMA (1.82 ms: 45 %% of the epilogue's samples on per-pixel residual loads) |" % R,
      "| `top_kernel_traffic.json` | DRAM bytes of those four launches (read by `bench.py` for `roofline.traffic`) |",
