@@ -29,7 +29,10 @@ L = ["# profiles/ -- measured evidence, round %s" % R[1:], "",
      "Everything here comes from one B200 box per call through `gpurun`; raw outputs land in `gpurun_out/` (scratch) and",
      "`tools/profile_round.sh` -> `tools/make_profiles.py` -> `tools/profiles_readme.py` turn them into these tracked files.",
      "Bench numbers are never taken under a profiler; ncu launch times are cold-cache and serialised (compare shares, not",
-     "absolutes).  Round-1 files (`*_r01_*`) are kept for comparison.", "",
+     "absolutes).  Round-1 files (`*_r01_*`) are kept for comparison.  One kernel changed after the per-call / ncu files",
+     "of this round were taken: the 32->1 output conv moved to 4-wide macro tiles (1.18 -> 1.01 ms per 16-event launch);",
+     "`bench_%s_sample16.json` (`roofline_candidates_ms`) was re-measured with it, `layers_%s_sample16.txt` and the" % (R, R),
+     "`[l32_1]` capture still show the 2-wide version.", "",
      "| File | What |", "|---|---|",
      "| `bench_%s_sample16.json` | default `python bench.py` line: Generator sampling, 16 events, + `train_step` (graph, 20 steps, per-step spread, CPU baseline) / `hbase3` / `roofline` (longest launch, chosen live) / `roofline_r1_dominant` / `roofline_best_kernel` / `stock_torch_gpu` / `cpu_baseline` |" % R,
      "| `bench_%s_train8_graph.json`, `_train8_eager.json`, `_train1_graph.json` | `--workload train`: the full G+D step, 8 events as a CUDA graph / launched kernel by kernel, and 1 event as a graph |" % R,
